@@ -1,0 +1,186 @@
+/*
+ * ss_b200.h -- C ABI of the B200-native subgraph-sketch engine (libss_b200.so, sm_100a).
+ *
+ * The reference (melifluos/subgraph-sketching) is pure Python; it has no FFI.  The boundary this
+ * library serves is the operator surface of `ElphHashes` in /root/reference/src/hashing.py: each entry
+ * point below names the reference function(s) it replaces.  A Python host binds these with `ctypes`
+ * (see INTEGRATION.md and subgraph_sketching_b200/_lib.py).
+ *
+ * Conventions
+ *   - every function is `extern "C"`, takes plain pointers / sizes, returns 0 on success, <0 on error;
+ *     `ss_last_error()` returns a thread-local message for the last failure on the calling thread
+ *   - all array pointers are DEVICE pointers (CUDA unified addressing) unless the name says `host`
+ *   - the caller owns every buffer, including workspaces; nothing is allocated or freed inside
+ *   - `stream` is a `cudaStream_t` passed as void*; calls only enqueue work, they never synchronise
+ *   - node ids are int64 in link lists / COO edges (as in the reference) and int32 inside the CSR
+ *
+ * Sketch record (the HBM layout, one per node per hop):
+ *     [ P_pad x uint32 MinHash | 2^p x uint8 HLL registers ]   P_pad = P rounded up to 4
+ *   = `ss_record_bytes(P, p)` bytes (768 B at the reference defaults P=128, p=8), 16-byte aligned.
+ *   The reference stores MinHash as int64 (values are < 2^32, hashing.py:59,122) and HLL as int8:
+ *   1280 B per node per hop.  `ss_pack_records` / `ss_unpack_records` convert between the two.
+ *   Record tables are addressed as (base pointer, row stride in bytes); stride >= record bytes and a
+ *   multiple of 16, so per-hop tables and node-major interleaved tables use the same entry points.
+ */
+#ifndef SS_B200_H
+#define SS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_ABI_VERSION 2
+
+#define SS_OK 0
+#define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
+#define SS_ERR_CUDA (-2)        /* a CUDA runtime call or kernel launch failed */
+#define SS_ERR_WORKSPACE (-3)   /* caller-provided workspace too small */
+
+/* flags for ss_link_features */
+#define SS_FLAG_USE_ZERO_ONE 1  /* keep the (0,1)/(1,0) [and K=3: (0,2)/(2,0)] columns; hashing.py:310-318 */
+#define SS_FLAG_FLOOR 2         /* clamp negative features to 0; hashing.py:319-320 */
+
+/* merge kernel variants (ss_khop_merge `variant`) */
+#define SS_MERGE_AUTO 0
+#define SS_MERGE_TMA 1          /* cp.async.bulk row staging through shared memory + mbarrier (P=128, p=8) */
+#define SS_MERGE_LDG 2          /* direct 128-bit global loads, register accumulators (P=128, p=8) */
+#define SS_MERGE_GENERIC 3      /* any (P, p): column-chunk outer loop, no staging */
+
+typedef void *ss_stream_t;
+
+/*
+ * HyperLogLog++ constants for one precision p.  They are INPUTS (the reference takes them from
+ * datasketch, hashing.py:69-80).  The struct lives in host memory; the three table pointers are device
+ * pointers.  `lc_table[z]` = linear-counting estimate for z empty registers, z = 0..m (entry 0 unused),
+ * computed by the host with the same float32 ops as hashing.py:194-195 so the LC regime is bit-exact.
+ */
+typedef struct ss_hll_consts {
+    int32_t p;             /* precision; m = 1 << p registers */
+    int32_t table_len;     /* T = length of raw_estimate / bias (>= 6) */
+    int32_t monotone;      /* 1 if raw_estimate is non-decreasing (enables the binary-search 6-NN) */
+    float threshold;       /* hashing.py:77 (float32 of the integer threshold) */
+    float alpha_m2;        /* float32(alpha * m * m), hashing.py:228 */
+    float five_m;          /* float32(5 * m), hashing.py:207 */
+    const float *lc_table; /* device, [m + 1] */
+    const float *raw_estimate; /* device, [T]  (hashing.py:80) */
+    const float *bias;         /* device, [T]  (hashing.py:79) */
+} ss_hll_consts;
+
+/* one hop of a sketch table as seen by the pairwise kernel */
+typedef struct ss_hop_view {
+    const void *records;   /* device; compact records of all nodes for this hop */
+    int64_t row_stride;    /* bytes between consecutive nodes */
+} ss_hop_view;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int ss_version(void);
+const char *ss_last_error(void);
+/* SM count and compute capability of the current device */
+int ss_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* bytes of one compact record; <0 if (num_perm, hll_p) is unsupported (need 1<=P<=4096, 4<=p<=18) */
+int64_t ss_record_bytes(int num_perm, int hll_p);
+
+/* ---- K1: hop-0 sketches ---------------------------------------------------------------------
+ * Replaces ElphHashes.initialise_minhash (hashing.py:118-124) and initialise_hll (hashing.py:126-137)
+ * for node ids first_id .. first_id+n-1 (the reference hashes ids 1..N, so first_id = 1 + row offset).
+ * perm_a/perm_b: device uint64 [P], the host-side RandomState(1) draws (hashing.py:106-116).
+ * log2_window:   device int32 [64]; entry k = largest j >= 0 such that the reference's float64
+ *                ceil(log2(2^k + j)) still evaluates to k (hashing.py:83-89), computed on the host with
+ *                numpy so the device reproduces the reference's bit_length quirk exactly.
+ * Returns SS_ERR_INVALID semantics of hashing.py:101-103 are impossible here: rank >= 1 always holds for
+ * 64-bit hashes, so no overflow error exists.
+ */
+int ss_init_records(int64_t n, int64_t first_id, int num_perm, int hll_p, const uint64_t *perm_a,
+                    const uint64_t *perm_b, const int32_t *log2_window, void *rec_out, int64_t out_stride,
+                    ss_stream_t stream);
+
+/* reference layout (int64 [n,P] MinHash, int8 [n,m] HLL)  <->  compact records; either side of the
+ * pair may be NULL to skip it.  These back `hash_table[k]['minhash']` / `['hll']` (hashing.py:153-154). */
+int ss_pack_records(const int64_t *minhash, const int8_t *hll, int64_t n, int num_perm, int hll_p,
+                    void *rec_out, int64_t out_stride, ss_stream_t stream);
+int ss_unpack_records(const void *rec, int64_t rec_stride, int64_t n, int num_perm, int hll_p,
+                      int64_t *minhash_out, int8_t *hll_out, ss_stream_t stream);
+
+/* ---- K6: COO -> CSR keyed by destination ------------------------------------------------------
+ * The reference scatters over the COO edge_index with self loops appended by
+ * add_self_loops(edge_index) (hashing.py:148; PyG flow source -> target, aggregation at edge_index[1]).
+ * Rows are destinations in [row_begin, row_begin + n_rows); a self loop (i, i) is added for every
+ * i < n_self_loops that falls in the row range.  Two steps because nnz of a row shard is data dependent:
+ *   ss_csr_rowptr : rowptr[0..n_rows] (int64, exclusive scan of in-degrees incl. self loops)
+ *   ss_csr_fill   : colidx[0..nnz) (int32 global source ids), order inside a row is unspecified
+ *                   (min/max merges are order independent)
+ * workspace: ss_csr_workspace_bytes(n_rows) bytes, 256-byte aligned, the same buffer for both calls.
+ */
+int64_t ss_csr_workspace_bytes(int64_t n_rows);
+int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops,
+                  int64_t row_begin, int64_t n_rows, int64_t *rowptr, void *workspace, int64_t workspace_bytes,
+                  ss_stream_t stream);
+int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops,
+                int64_t row_begin, int64_t n_rows, const int64_t *rowptr, int32_t *colidx, void *workspace,
+                int64_t workspace_bytes, ss_stream_t stream);
+
+/* ---- K2: one hop of sketch propagation ----------------------------------------------------------
+ * Replaces MinhashPropagation.forward + HllPropagation.forward (hashing.py:28-45, called at :160-162)
+ * and, when cards_out != NULL, the hll_count of the merged rows (hashing.py:163).
+ *   rec_out[r] = ( min over c in colidx[rowptr[r]..rowptr[r+1]) of rec_in[c].minhash,
+ *                  max ...                                      of rec_in[c].hll )
+ *   rows with no in-edge are all-zero (scatter-max fill).
+ * rec_in is the full previous-hop table (indexed by global id), rec_out holds the n_rows owned rows
+ * (rowptr is local to them: rowptr[0] = 0, rowptr[n_rows] = nnz); rec_in and rec_out must not overlap.
+ * cards_out[r * cards_stride] receives the float32 HLL++ estimate of row r (stride in elements).
+ * workspace: ss_merge_workspace_bytes(nnz, P, p) bytes, 16-byte aligned.  The neighbour list is cut into
+ * equal ranges; rows cut by a range boundary leave partial records there and a fix-up launch folds them,
+ * so power-law hubs cost no more per neighbour than any other row.
+ */
+int64_t ss_merge_workspace_bytes(int64_t nnz, int num_perm, int hll_p);
+int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
+                  int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p, void *workspace,
+                  int64_t workspace_bytes, float *cards_out, int64_t cards_stride, const ss_hll_consts *hc,
+                  int variant, ss_stream_t stream);
+
+/* operator forms on the reference's own tensor layouts (ELPH calls these per batch,
+ * /root/reference/src/models/elph.py:209-212): element-wise signed min (int64) / max (int8) over
+ * in-neighbours; rows with no in-edge are 0.  colidx == NULL means neighbour j of row r is row
+ * rowptr[r] + j of x (used for hll_neighbour_merge / minhash_neighbour_merge, hashing.py:239-245). */
+int ss_prop_min_i64(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *x,
+                    int64_t *out, int64_t width, ss_stream_t stream);
+int ss_prop_max_i8(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int8_t *x, int8_t *out,
+                   int64_t width, ss_stream_t stream);
+
+/* ---- K3: HyperLogLog++ cardinality ---------------------------------------------------------------
+ * Replaces ElphHashes.hll_count (hashing.py:212-232) with _linearcounting (:194-195),
+ * _estimate_bias (:197-204) and _refine_hll_count_estimate (:206-210).
+ * regs: uint8 rows of m registers, `row_stride` bytes apart (8-byte aligned); out[i * out_stride] float32.
+ */
+int ss_hll_count(const void *regs, int64_t row_stride, int64_t n, const ss_hll_consts *hc, float *out,
+                 int64_t out_stride, ss_stream_t stream);
+/* _estimate_bias alone (hashing.py:197-204): out[i] = mean bias of the 6 nearest raw estimates to e[i] */
+int ss_estimate_bias(const float *e, int64_t n, const ss_hll_consts *hc, float *out, ss_stream_t stream);
+
+/* ---- K5: small row-wise helpers ---------------------------------------------------------------------
+ * jaccard (hashing.py:247-256): out[i] = count(src[i,:] == dst[i,:]) / denom, int64 rows of `width` slots
+ *   (the reference divides by num_perm whatever the width).
+ * hll merge (hashing.py:234-237): element-wise max of two int8 arrays of `count` bytes. */
+int ss_jaccard_i64(const int64_t *src, const int64_t *dst, int64_t n, int64_t width, int64_t denom, float *out,
+                   ss_stream_t stream);
+int ss_max_i8(const int8_t *a, const int8_t *b, int64_t count, int8_t *out, ss_stream_t stream);
+
+/* ---- K4: pairwise structural features ---------------------------------------------------------------
+ * Replaces ElphHashes.get_subgraph_features (hashing.py:258-323) incl. _get_intersections (:167-189),
+ * jaccard (:247-256) and _hll_merge (:234-237).
+ *   links        int64 [L, 2] (u, v) global node ids
+ *   hops         HOST array of K+1 views indexed by hop (entry 0 is ignored)
+ *   cards        float32, cards[node * cards_stride + (k-1)] = k-hop cardinality (hashing.py:163)
+ *   features_out float32 [L, K(K+2)] or NULL;  inter_out float32 [L, K*K] (row-major (k1-1)*K+(k2-1)) or NULL
+ */
+int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *hops, int max_hops,
+                     int num_perm, int hll_p, const float *cards, int64_t cards_stride,
+                     const ss_hll_consts *hc, int flags, float *features_out, float *inter_out,
+                     ss_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SS_B200_H */

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY.  Writes tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/src/hashing.py behind oracle/stubs) on small seeded inputs.
+
+Run in the build container (the GPU box has no /root/reference):   python -m oracle.make_golden
+Every case stores its inputs and the reference's outputs, so the parity tests need nothing but the file.
+The HLL++ bias tables the reference saw (packaged Monte-Carlo tables served by the datasketch stub, or
+real datasketch if installed -- recorded in `tables_source`) are stored too and injected into the engine
+and the oracle restatement by the tests.
+"""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+from oracle import ref_loader  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+
+def ring(n):
+    i = torch.arange(n)
+    return torch.stack([torch.cat([i, (i + 1) % n]), torch.cat([(i + 1) % n, i])])
+
+
+def barabasi_albert(n, m, seed):
+    """undirected BA graph, both directions listed (the reference fixture is a 30-node BA graph,
+    test/test_hashing.py:21-33)"""
+    rng = np.random.RandomState(seed)
+    targets = list(range(m))
+    repeated = []
+    src, dst = [], []
+    for v in range(m, n):
+        for t in set(targets):
+            src += [v, t]
+            dst += [t, v]
+        repeated += list(set(targets)) + [v] * m
+        targets = [repeated[i] for i in rng.randint(0, len(repeated), size=m)]
+    return torch.tensor([src, dst], dtype=torch.int64)
+
+
+def random_directed(n, e, seed, max_id=None):
+    g = torch.Generator().manual_seed(seed)
+    hi = n if max_id is None else max_id
+    ei = torch.randint(0, hi, (2, e), generator=g)
+    return ei
+
+
+CASES = [
+    # name, num_nodes, edge_index, K, P, p, n_links
+    ('ring12_k3', 12, ring(12), 3, 128, 8, 40),
+    ('ring12_k1', 12, ring(12), 1, 128, 8, 40),
+    ('ba30_k2', 30, barabasi_albert(30, 3, 0), 2, 128, 8, 120),
+    ('ba300_k3', 300, barabasi_albert(300, 8, 1), 3, 128, 8, 400),
+    ('directed_dups_k2', 200, random_directed(200, 1500, 2), 2, 128, 8, 300),
+    ('isolated_tail_k3', 260, random_directed(260, 1200, 3, max_id=200), 3, 128, 8, 300),
+    ('dense_hub_k2', 3000, torch.cat([random_directed(3000, 9000, 4),
+                                      torch.stack([torch.arange(1, 3000), torch.zeros(2999, dtype=torch.int64)]),
+                                      torch.stack([torch.zeros(2999, dtype=torch.int64), torch.arange(1, 3000)])],
+                                     dim=1), 2, 128, 8, 600),
+    ('generic_p4_P8_k2', 120, random_directed(120, 500, 5), 2, 8, 4, 200),
+    ('generic_p6_P33_k3', 150, random_directed(150, 900, 6), 3, 33, 6, 200),
+    ('generic_p10_P64_k2', 400, barabasi_albert(400, 10, 7), 2, 64, 10, 300),
+]
+
+
+def main():
+    ref = ref_loader.load()
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for name, n, ei, K, P, p, n_links in CASES:
+        blob = {'num_nodes': n, 'edge_index': ei.numpy(), 'K': K, 'P': P, 'p': p,
+                'tables_source': 'stub' if ref_loader.USING_STUBS.get('datasketch') else 'datasketch'}
+        g = torch.Generator().manual_seed(100 + n)
+        links = torch.randint(0, n, (n_links, 2), generator=g)
+        links[0] = torch.tensor([0, 1])
+        links[1] = torch.tensor([3, 3])  # self link
+        if ei.shape[1] >= 8:
+            links[2:10] = ei[:, :8].t()  # true edges
+        blob['links'] = links.numpy()
+        for zo in (False, True):
+            for fl in (False, True):
+                args = Namespace(max_hash_hops=K, floor_sf=fl, minhash_num_perm=P, hll_p=p, use_zero_one=zo)
+                eh = ref.ElphHashes(args)
+                tables, cards = eh.build_hash_tables(n, ei)
+                feats = eh.get_subgraph_features(links, tables, cards)
+                blob[f'features_zo{int(zo)}_fl{int(fl)}'] = feats.numpy()
+        inter = eh._get_intersections(links, tables)
+        blob['intersections'] = torch.stack([inter[(a, b)] for a in range(1, K + 1) for b in range(1, K + 1)],
+                                            dim=1).numpy()
+        blob['cards'] = cards.numpy()
+        for k in range(K + 1):
+            blob[f'minhash_{k}'] = tables[k]['minhash'].numpy().astype(np.uint32)
+            blob[f'hll_{k}'] = tables[k]['hll'].numpy()
+        blob['hll_threshold'] = eh.hll_threshold
+        blob['estimate_vector'] = eh.estimate_vector.numpy()
+        blob['bias_vector'] = eh.bias_vector.numpy()
+        path = os.path.join(OUT_DIR, name + '.npz')
+        np.savez_compressed(path, **blob)
+        print(f'{name}: N={n} E={ei.shape[1]} K={K} P={P} p={p} L={n_links} -> {os.path.getsize(path)} bytes',
+              flush=True)
+    # hll_count known answers across regimes (all-equal registers, partial fills, bias regime sweep)
+    args = Namespace(max_hash_hops=2, floor_sf=False, minhash_num_perm=128, hll_p=8, use_zero_one=False)
+    eh = ref.ElphHashes(args)
+    rng = np.random.RandomState(11)
+    rows = [np.full(256, 3), np.concatenate([np.ones(100), np.zeros(156)])]
+    for fill in (1, 5, 30, 90, 150, 200, 230, 250, 255, 256):
+        for hi in (2, 4, 8, 16, 40):
+            r = np.zeros(256)
+            idx = rng.permutation(256)[:fill]
+            r[idx] = rng.randint(1, hi + 1, size=fill)
+            rows.append(r)
+    regs = torch.tensor(np.stack(rows), dtype=torch.int8)
+    counts = eh.hll_count(regs)
+    e = torch.linspace(150., 1500., 400)
+    bias = eh._estimate_bias(e)
+    np.savez_compressed(os.path.join(OUT_DIR, 'hll_count_p8.npz'), regs=regs.numpy(), counts=counts.numpy(),
+                        e=e.numpy(), bias=bias.numpy(), hll_threshold=eh.hll_threshold,
+                        estimate_vector=eh.estimate_vector.numpy(), bias_vector=eh.bias_vector.numpy())
+    print('hll_count_p8 written')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,100 @@
+"""ctypes binding of libss_b200.so (the C ABI declared in include/ss_b200.h).
+
+The library is the product: there is no Python or CPU fallback.  If the shared object has not been built
+(`python -c "import __graft_entry__ as g; g.build()"` or `make -C subgraph_sketching_b200/csrc`) importing
+this module raises, and every compute entry point raises when no CUDA device is present.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
+
+SS_ABI_VERSION = 2
+SS_FLAG_USE_ZERO_ONE = 1
+SS_FLAG_FLOOR = 2
+SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC = 0, 1, 2, 3
+MERGE_VARIANTS = {'auto': SS_MERGE_AUTO, 'tma': SS_MERGE_TMA, 'ldg': SS_MERGE_LDG, 'generic': SS_MERGE_GENERIC}
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_ptr = ctypes.c_void_p
+
+
+class HllConsts(ctypes.Structure):
+    """struct ss_hll_consts"""
+    _fields_ = [('p', ctypes.c_int32), ('table_len', ctypes.c_int32), ('monotone', ctypes.c_int32),
+                ('threshold', ctypes.c_float), ('alpha_m2', ctypes.c_float), ('five_m', ctypes.c_float),
+                ('lc_table', c_ptr), ('raw_estimate', c_ptr), ('bias', c_ptr)]
+
+
+class HopView(ctypes.Structure):
+    """struct ss_hop_view"""
+    _fields_ = [('records', c_ptr), ('row_stride', c_i64)]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/ss_b200.h
+SIGNATURES = {
+    'ss_version': (c_int, []),
+    'ss_last_error': (ctypes.c_char_p, []),
+    'ss_device_info': (c_int, [ctypes.POINTER(c_int)] * 3),
+    'ss_record_bytes': (c_i64, [c_int, c_int]),
+    'ss_init_records': (c_int, [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_pack_records': (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr]),
+    'ss_unpack_records': (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    'ss_csr_workspace_bytes': (c_i64, [c_i64]),
+    'ss_csr_rowptr': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_csr_fill': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_merge_workspace_bytes': (c_i64, [c_i64, c_int, c_int]),
+    'ss_khop_merge': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64,
+                              c_ptr, c_i64, ctypes.POINTER(HllConsts), c_int, c_ptr]),
+    'ss_prop_min_i64': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_prop_max_i8': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_hll_count': (c_int, [c_ptr, c_i64, c_i64, ctypes.POINTER(HllConsts), c_ptr, c_i64, c_ptr]),
+    'ss_estimate_bias': (c_int, [c_ptr, c_i64, ctypes.POINTER(HllConsts), c_ptr, c_ptr]),
+    'ss_jaccard_i64': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    'ss_max_i8': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    'ss_link_features': (c_int, [c_ptr, c_i64, ctypes.POINTER(HopView), c_int, c_int, c_int, c_ptr, c_i64,
+                                 ctypes.POINTER(HllConsts), c_int, c_ptr, c_ptr, c_ptr]),
+}
+
+
+class SketchLibError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise SketchLibError(
+            f'{LIB_PATH} is missing: build the CUDA library first (make -C {os.path.join(_HERE, "csrc")} or '
+            '__graft_entry__.build()).  There is no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    ver = lib.ss_version()
+    if ver != SS_ABI_VERSION:
+        raise SketchLibError(f'libss_b200.so ABI version {ver} != expected {SS_ABI_VERSION}; rebuild it')
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=''):
+    """raise on a negative return code from the library"""
+    if rc is not None and rc < 0:
+        msg = lib.ss_last_error()
+        msg = msg.decode() if msg else ''
+        if rc == -1:
+            raise ValueError(f'{what}: {msg}')
+        raise SketchLibError(f'{what} failed (code {rc}): {msg}')
+    return rc
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise SketchLibError('subgraph_sketching_b200 needs a CUDA device (sm_100a); none is visible and there is '
+                             'no CPU fallback')

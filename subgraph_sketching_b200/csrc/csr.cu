@@ -1,0 +1,241 @@
+// csr.cu -- K6: destination-keyed CSR from the reference's COO edge_index (+ implicit self loops).
+//
+// The reference never builds a CSR: PyG scatters over the COO list after add_self_loops(edge_index)
+// (/root/reference/src/hashing.py:148; flow source -> target, reduction at edge_index[1]).  A pull-style
+// merge needs in-neighbours per destination, so: histogram of destinations -> exclusive scan -> fill with
+// per-row cursors.  Order inside a row is arbitrary (min/max are order independent).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ss {
+
+constexpr int SCAN_ITEMS = 4;                   // per thread
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_BLOCK;  // rows per block
+
+struct CsrWorkspace {
+    uint32_t *deg;       // [n_rows]  in-degree histogram, later the fill cursors
+    int64_t *tile_sum;   // [n_tiles] per-tile totals, then exclusive tile offsets
+    int64_t n_tiles;
+};
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static int64_t n_tiles_for(int64_t n_rows) { return (n_rows + SCAN_TILE - 1) / SCAN_TILE; }
+
+static int64_t workspace_bytes(int64_t n_rows) {
+    return align_up(n_rows * 4, 256) + align_up((n_tiles_for(n_rows) + 1) * 8, 256);
+}
+
+static CsrWorkspace carve(void *ws, int64_t n_rows) {
+    CsrWorkspace w;
+    w.deg = (uint32_t *)ws;
+    w.tile_sum = (int64_t *)((char *)ws + align_up(n_rows * 4, 256));
+    w.n_tiles = n_tiles_for(n_rows);
+    return w;
+}
+
+__global__ void __launch_bounds__(256) degree_kernel(const int64_t *__restrict__ dst, int64_t n_edges,
+                                                      int64_t row_begin, int64_t n_rows, uint32_t *deg) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t d = dst[e] - row_begin;
+        if (d >= 0 && d < n_rows) atomicAdd(deg + d, 1u);
+    }
+}
+
+__device__ __forceinline__ int64_t row_degree(const uint32_t *deg, int64_t r, int64_t n_rows, int64_t row_begin,
+                                              int64_t n_self_loops) {
+    if (r >= n_rows) return 0;
+    return (int64_t)deg[r] + ((row_begin + r) < n_self_loops ? 1 : 0);
+}
+
+__device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t *smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    int64_t t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += smem[w];
+    __syncthreads();
+    return t;
+}
+
+// phase 1: total of each tile of SCAN_TILE rows
+__global__ void __launch_bounds__(SCAN_BLOCK) tile_sum_kernel(const uint32_t *__restrict__ deg, int64_t n_rows,
+                                                               int64_t row_begin, int64_t n_self_loops,
+                                                               int64_t *__restrict__ tile_sum) {
+    __shared__ int64_t sm[SCAN_BLOCK / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) v += row_degree(deg, base + k, n_rows, row_begin, n_self_loops);
+    int64_t t = block_sum_i64(v, sm);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = t;
+}
+
+// phase 2: one block turns the tile totals into exclusive offsets (serial over chunks of blockDim tiles)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int64_t *tile_sum, int64_t n_tiles) {
+    __shared__ int64_t warp_tot[32];
+    __shared__ int64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_tiles; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t x = (i < n_tiles) ? tile_sum[i] : 0;
+        int64_t inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = warp_tot[lane];
+            int64_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(FULL, winc, o);
+                if (lane >= o) winc += y;
+            }
+            warp_tot[lane] = winc - w;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t excl = carry + warp_tot[warp] + inc - x;
+        if (i < n_tiles) tile_sum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sum[n_tiles] = carry_s;  // grand total
+}
+
+// phase 3: exclusive scan inside each tile + tile offset -> rowptr
+__global__ void __launch_bounds__(SCAN_BLOCK) rowptr_kernel(const uint32_t *__restrict__ deg, int64_t n_rows,
+                                                             int64_t row_begin, int64_t n_self_loops,
+                                                             const int64_t *__restrict__ tile_off,
+                                                             int64_t *__restrict__ rowptr) {
+    __shared__ int64_t warp_tot[SCAN_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t d[SCAN_ITEMS];
+    int64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        d[k] = row_degree(deg, base + k, n_rows, row_begin, n_self_loops);
+        v += d[k];
+    }
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t y = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int64_t off = tile_off[blockIdx.x];
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    int64_t run = off + inc - v;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n_rows) rowptr[base + k] = run;
+        run += d[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) rowptr[n_rows] = tile_off[gridDim.x];
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                                    int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
+                                                    int64_t n_rows, const int64_t *__restrict__ rowptr,
+                                                    uint32_t *cursor, int32_t *__restrict__ colidx) {
+    const int64_t total = n_edges + n_rows;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t d, s;
+        if (t < n_edges) {
+            d = dst[t] - row_begin;
+            s = src[t];
+            if (d < 0 || d >= n_rows) continue;
+        } else {
+            d = t - n_edges;
+            s = row_begin + d;
+            if (s >= n_self_loops) continue;
+        }
+        uint32_t k = atomicAdd(cursor + d, 1u);
+        colidx[rowptr[d] + k] = (int32_t)s;
+    }
+}
+
+}  // namespace ss
+
+extern "C" {
+
+int64_t ss_csr_workspace_bytes(int64_t n_rows) {
+    if (n_rows < 0) return SS_ERR_INVALID;
+    return ss::workspace_bytes(n_rows);
+}
+
+int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
+                  int64_t n_rows, int64_t *rowptr, void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+    (void)src;
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_self_loops >= 0 && row_begin >= 0, "negative size passed to ss_csr_rowptr");
+    SS_REQUIRE(rowptr && workspace, "null pointer passed to ss_csr_rowptr");
+    SS_REQUIRE(n_edges == 0 || dst, "dst is null");
+    SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    if (workspace_bytes < ss::workspace_bytes(n_rows)) {
+        ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes,
+                      (long long)ss::workspace_bytes(n_rows));
+        return SS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0) {
+        SS_CUDA(cudaMemsetAsync(rowptr, 0, 8, st));
+        return SS_OK;
+    }
+    ss::CsrWorkspace w = ss::carve(workspace, n_rows);
+    SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
+    if (n_edges > 0) {
+        int64_t blocks = (n_edges + 255) / 256;
+        int64_t cap = (int64_t)ss::sm_count() * 32;
+        ss::degree_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(dst, n_edges, row_begin, n_rows, w.deg);
+        SS_LAUNCH_CHECK("degree_kernel");
+    }
+    ss::tile_sum_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, w.tile_sum);
+    SS_LAUNCH_CHECK("tile_sum_kernel");
+    ss::tile_scan_kernel<<<1, 1024, 0, st>>>(w.tile_sum, w.n_tiles);
+    SS_LAUNCH_CHECK("tile_scan_kernel");
+    ss::rowptr_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, w.tile_sum, rowptr);
+    SS_LAUNCH_CHECK("rowptr_kernel");
+    return SS_OK;
+}
+
+int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
+                int64_t n_rows, const int64_t *rowptr, int32_t *colidx, void *workspace, int64_t workspace_bytes,
+                ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_self_loops >= 0 && row_begin >= 0, "negative size passed to ss_csr_fill");
+    SS_REQUIRE(rowptr && workspace, "null pointer passed to ss_csr_fill");
+    SS_REQUIRE(n_edges == 0 || (src && dst), "src/dst is null");
+    SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    if (workspace_bytes < ss::workspace_bytes(n_rows)) {
+        ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes,
+                      (long long)ss::workspace_bytes(n_rows));
+        return SS_ERR_WORKSPACE;
+    }
+    if (n_rows == 0) return SS_OK;
+    SS_REQUIRE(colidx, "colidx is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    ss::CsrWorkspace w = ss::carve(workspace, n_rows);
+    SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
+    int64_t total = n_edges + n_rows;
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)ss::sm_count() * 32;
+    ss::fill_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(src, dst, n_edges, n_self_loops, row_begin, n_rows,
+                                                                       rowptr, w.deg, colidx);
+    SS_LAUNCH_CHECK("fill_kernel");
+    return SS_OK;
+}
+
+}  // extern "C"

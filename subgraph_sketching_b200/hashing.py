@@ -1,0 +1,645 @@
+"""B200-native drop-in for /root/reference/src/hashing.py (`ElphHashes`, `MinhashPropagation`,
+`HllPropagation`, `LABEL_LOOKUP`).
+
+Same names, arguments, return types and error behaviour as the reference class; every array computation is
+a hand-written sm_100a kernel in libss_b200.so reached through the ctypes C ABI (include/ss_b200.h).  torch
+is used for device memory, streams and host<->device copies only.  There is no CPU fallback: the module
+raises if the library is missing or no CUDA device is visible.
+
+Device semantics (reference: hashing.py is device-agnostic torch)
+  * CUDA inputs  -> kernels run on that device / the current stream, outputs stay there (the ELPH path,
+    models/elph.py:190-213, train.py:199-204)
+  * CPU inputs   -> transparent offload: pinned H2D copy, kernels, D2H copy; the result lives on the input's
+    device exactly as in the reference (the BUDDY preprocessing path, datasets/elph.py:85,200,207)
+
+Internal layout: one compact 768-byte record per node per hop ([128 x uint32 MinHash | 256 x uint8 HLL]).
+`build_hash_tables` returns a `SketchTables` mapping that holds the records on the GPU and materialises the
+reference's int64 / int8 tensors only when `table[k]['minhash']` / `['hll']` is indexed; it pickles
+(`torch.save`) as the reference's plain dict-of-dict of CPU tensors, so on-disk caches interoperate.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import os
+from time import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HllConsts, HopView, check, lib
+
+logger = logging.getLogger(__name__)
+logger.setLevel(logging.INFO)
+
+# feature index -> (hops from u, hops from v), keyed by max hops  (hashing.py:22-25)
+LABEL_LOOKUP = {1: {0: (1, 1), 1: (0, 1), 2: (1, 0)},
+                2: {0: (1, 1), 1: (2, 1), 2: (1, 2), 3: (2, 2), 4: (0, 1), 5: (1, 0), 6: (0, 2), 7: (2, 0)},
+                3: {0: (1, 1), 1: (2, 1), 2: (1, 2), 3: (2, 2), 4: (3, 1), 5: (1, 3), 6: (3, 2), 7: (2, 3), 8: (3, 3),
+                    9: (0, 1), 10: (1, 0), 11: (0, 2), 12: (2, 0), 13: (0, 3), 14: (3, 0)}}
+
+_TABLES_PATH = os.environ.get('SS_B200_HLLPP_TABLES') or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), 'data', 'hllpp_tables.npz')
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _cuda_device(t=None):
+    """device the kernels run on for input `t` (its own device if CUDA, else the current CUDA device)"""
+    _lib.require_cuda()
+    if t is not None and t.is_cuda:
+        return t.device
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _to_device(t, device):
+    if t.device == device:
+        return t
+    if t.device.type == 'cpu' and t.numel() > (1 << 16) and not t.is_pinned():
+        try:
+            t = t.pin_memory()
+        except RuntimeError:  # pinning can fail on tiny / exotic hosts; the pageable copy is still correct
+            pass
+    return t.to(device, non_blocking=True)
+
+
+def hllpp_tables(p):
+    """(threshold, raw_estimate[T], bias[T]) for precision p: from `datasketch` when it is importable
+    (what the reference reads, hashing.py:77-80), else from the packaged Monte-Carlo tables
+    (tools/gen_hllpp_tables.py)."""
+    try:
+        from datasketch import hyperloglog_const as hc
+        return hc._thresholds[p - 4], list(hc._raw_estimate[p - 4]), list(hc._bias[p - 4])
+    except ImportError:
+        blob = np.load(_TABLES_PATH)
+        return int(blob['thresholds'][p - 4]), blob[f'raw_estimate_p{p}'], blob[f'bias_p{p}']
+
+
+def hll_alpha(p):
+    """HyperLogLog alpha_m (datasketch.HyperLogLogPlusPlus.alpha; hashing.py:72)"""
+    if p == 4:
+        return 0.673
+    if p == 5:
+        return 0.697
+    if p == 6:
+        return 0.709
+    return 0.7213 / (1.0 + 1.079 / (1 << p))
+
+
+def log2_window_table():
+    """int32[64]: entry k = largest j >= 0 with ceil(log2(float64(2^k + j))) == k, i.e. how far above a power
+    of two the reference's float64 `_np_bit_length` (hashing.py:83-89) still rounds DOWN.  Evaluated with
+    numpy itself so that the device rank computation reproduces the reference bit for bit."""
+    out = np.zeros(64, dtype=np.int32)
+    for k in range(1, 63):
+        base = 1 << k
+
+        def rounds_down(j):
+            return int(np.ceil(np.log2(np.array([base + j], dtype=np.uint64)))[0]) == k
+
+        if not rounds_down(1):
+            continue
+        lo, hi = 1, base  # rounds_down(lo) holds; 2^k + base = 2^(k+1) never rounds down
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if rounds_down(mid):
+                lo = mid
+            else:
+                hi = mid
+        out[k] = min(lo, np.iinfo(np.int32).max)
+    return out
+
+
+class _CsrCache(object):
+    """destination-keyed CSR of one edge_index, cached on identity so that ELPH's per-batch
+    hll_prop/minhash_prop calls (models/elph.py:209-212) build it once"""
+
+    def __init__(self):
+        self.key = None
+        self.value = None
+
+    def get(self, edge_index, device, add_loops):
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(device), add_loops)
+        if key == self.key:
+            return self.value
+        self.value = build_csr(edge_index, device, add_loops=add_loops)
+        self.key = key
+        return self.value
+
+
+def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0):
+    """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [nnz], nnz) keyed by destination
+    (PyG flow source -> target, hashing.py:30-35).  With add_loops, a self loop is appended for every node id
+    < max(edge_index)+1, which is add_self_loops(edge_index) without num_nodes (hashing.py:148)."""
+    ei = _to_device(edge_index, device)
+    if ei.dtype != torch.int64:
+        ei = ei.long()
+    ei = ei.contiguous()
+    n_edges = ei.shape[1]
+    max_id = int(ei.max()) if n_edges else -1
+    n_loops = (max_id + 1) if add_loops else 0
+    if num_rows is None:
+        num_rows = max_id + 1
+    src, dst = ei[0], ei[1]
+    ws_bytes = check(lib.ss_csr_workspace_bytes(num_rows), 'ss_csr_workspace_bytes')
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
+    rowptr = torch.empty(num_rows + 1, dtype=torch.int64, device=device)
+    st = _stream_ptr(device)
+    check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, n_loops, row_begin, num_rows, _ptr(rowptr), _ptr(ws),
+                            ws.numel(), st), 'ss_csr_rowptr')
+    nnz = int(rowptr[-1])
+    colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)
+    check(lib.ss_csr_fill(_ptr(src), _ptr(dst), n_edges, n_loops, row_begin, num_rows, _ptr(rowptr), _ptr(colidx),
+                          _ptr(ws), ws.numel(), st), 'ss_csr_fill')
+    return rowptr, colidx, nnz, max_id
+
+
+class MinhashPropagation(object):
+    """element-wise min over in-neighbours (hashing.py:28-35).  `edge_index` already holds the self loops."""
+
+    def __init__(self, owner=None):
+        self._csr = _CsrCache()
+
+    @torch.no_grad()
+    def __call__(self, x, edge_index):
+        return self.forward(x, edge_index)
+
+    @torch.no_grad()
+    def forward(self, x, edge_index):
+        return _propagate(x, edge_index, self._csr, is_min=True)
+
+
+class HllPropagation(object):
+    """register-wise max over in-neighbours (hashing.py:38-45)"""
+
+    def __init__(self, owner=None):
+        self._csr = _CsrCache()
+
+    @torch.no_grad()
+    def __call__(self, x, edge_index):
+        return self.forward(x, edge_index)
+
+    @torch.no_grad()
+    def forward(self, x, edge_index):
+        return _propagate(x, edge_index, self._csr, is_min=False)
+
+
+def _propagate(x, edge_index, cache, is_min):
+    device = _cuda_device(x)
+    want = torch.int64 if is_min else torch.int8
+    xd = _to_device(x, device)
+    if xd.dtype != want:
+        xd = xd.to(want)
+    xd = xd.contiguous()
+    n, width = xd.shape
+    rowptr, colidx, nnz, max_id = cache.get(edge_index, device, False)
+    if max_id >= n:
+        raise IndexError(f'edge_index refers to node {max_id} but x has {n} rows')
+    if rowptr.numel() - 1 < n:  # nodes above max(edge_index): no in-edges -> zero rows
+        pad = rowptr[-1:].expand(n - (rowptr.numel() - 1))
+        rowptr = torch.cat([rowptr, pad])
+    out = torch.empty_like(xd)
+    fn = lib.ss_prop_min_i64 if is_min else lib.ss_prop_max_i8
+    check(fn(_ptr(rowptr), _ptr(colidx), n, _ptr(xd), _ptr(out), width, _stream_ptr(device)), 'ss_prop')
+    out = out.to(x.dtype) if out.dtype != x.dtype else out
+    return out if x.device == device else out.to(x.device)
+
+
+class HopSketch(object):
+    """one hop of a SketchTables: behaves like {'hll': int8 [N, m], 'minhash': int64 [N, P]}"""
+
+    def __init__(self, records, num_perm, p, out_device):
+        self.records = records  # uint8 [N, record_bytes] on the GPU
+        self.num_perm = num_perm
+        self.p = p
+        self.out_device = out_device
+        self._cache = {}
+
+    def keys(self):
+        return ['hll', 'minhash']
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return 2
+
+    def __contains__(self, key):
+        return key in ('hll', 'minhash')
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def __getitem__(self, key):
+        if key not in ('hll', 'minhash'):
+            raise KeyError(key)
+        if key not in self._cache:
+            rec = self.records
+            n = rec.shape[0]
+            dev = rec.device
+            with torch.cuda.device(dev):
+                if key == 'minhash':
+                    out = torch.empty((n, self.num_perm), dtype=torch.int64, device=dev)
+                    check(lib.ss_unpack_records(_ptr(rec), rec.stride(0), n, self.num_perm, self.p, _ptr(out), None,
+                                                _stream_ptr(dev)), 'ss_unpack_records')
+                else:
+                    out = torch.empty((n, 1 << self.p), dtype=torch.int8, device=dev)
+                    check(lib.ss_unpack_records(_ptr(rec), rec.stride(0), n, self.num_perm, self.p, None, _ptr(out),
+                                                _stream_ptr(dev)), 'ss_unpack_records')
+            self._cache[key] = out.to(self.out_device)
+        return self._cache[key]
+
+    def as_dict(self, device='cpu'):
+        return {'hll': self['hll'].to(device), 'minhash': self['minhash'].to(device)}
+
+
+class SketchTables(dict):
+    """{hop: HopSketch} for hop = 0..K.  Pickles as the reference's plain dict of CPU tensors."""
+
+    def __init__(self, hops, num_perm, p):
+        super().__init__(hops)
+        self.num_perm = num_perm
+        self.p = p
+
+    def records(self, k):
+        return dict.__getitem__(self, k).records
+
+    def __reduce__(self):
+        # pickle exactly like a plain (Ordered)dict of {'hll', 'minhash'} CPU tensors: loadable by torch.load
+        # with weights_only=True and by the reference, without this package
+        import collections
+        plain = [(k, dict.__getitem__(self, k).as_dict('cpu')) for k in sorted(self.keys())]
+        return (collections.OrderedDict, (), None, None, iter(plain))
+
+
+class ElphHashes(object):
+    """
+    class to store hashes and retrieve subgraph features -- B200 engine behind the reference's API
+    (hashing.py:48-323)
+    """
+
+    def __init__(self, args, hll_tables=None, merge_variant='auto'):
+        assert args.max_hash_hops in {1, 2, 3}, f'hashing is not implemented for {args.max_hash_hops} hops'
+        self.max_hops = args.max_hash_hops
+        self.floor_sf = args.floor_sf  # if true set minimum sf to 0 (they're counts, so it should be)
+        # minhash params (hashing.py:57-62)
+        self._mersenne_prime = np.uint64((1 << 61) - 1)
+        self._max_minhash = np.uint64((1 << 32) - 1)
+        self._minhash_range = (1 << 32)
+        self.minhash_seed = 1
+        self.num_perm = args.minhash_num_perm
+        self.minhash_prop = MinhashPropagation()
+        # hll params (hashing.py:64-81)
+        self.p = args.hll_p
+        self.m = 1 << self.p
+        self.use_zero_one = args.use_zero_one
+        self.label_lookup = LABEL_LOOKUP[self.max_hops]
+        if not 4 <= self.p <= 18:
+            raise ValueError('p must be in [4, 18]')
+        self.hll_hashfunc = None  # the reference stores datasketch's sha1 hashfunc but never calls it
+        self.alpha = hll_alpha(self.p)
+        self.max_rank = 64 - self.p
+        self.hll_size = self.m
+        if hll_tables is None:
+            hll_tables = hllpp_tables(self.p)
+        threshold, raw_estimate, bias = hll_tables
+        self.hll_threshold = threshold
+        self.bias_vector = torch.tensor(np.asarray(bias, dtype=np.float64), dtype=torch.float)
+        self.estimate_vector = torch.tensor(np.asarray(raw_estimate, dtype=np.float64), dtype=torch.float)
+        self.hll_prop = HllPropagation()
+        self.merge_variant = merge_variant
+        self.validate_links = True  # bounds-check link endpoints (the reference raises IndexError)
+        # linear-counting table, evaluated with the reference's own float32 torch expression (hashing.py:195)
+        nz = torch.arange(1, self.m + 1, dtype=torch.int64)
+        self._lc_host = torch.cat([torch.zeros(1), self.m * torch.log(self.m / nz)]).float()
+        self._dev = {}  # per-device constants
+
+    # ------------------------------------------------------------------ device constants
+    def _consts(self, device):
+        key = str(device)
+        d = self._dev.get(key)
+        if d is None or d['est_src'] is not self.estimate_vector or d['bias_src'] is not self.bias_vector:
+            est = self.estimate_vector.float().contiguous()
+            bias = self.bias_vector.float().contiguous()
+            if est.numel() != bias.numel() or est.numel() < 6:
+                raise ValueError('estimate_vector / bias_vector must have the same length >= 6')
+            ab = self._init_permutations(self.num_perm)
+            d = {
+                'est_src': self.estimate_vector, 'bias_src': self.bias_vector,
+                'lc': self._lc_host.to(device), 'est': est.to(device), 'bias': bias.to(device),
+                'perm_a': torch.from_numpy(ab[0].astype(np.int64)).to(device),
+                'perm_b': torch.from_numpy(ab[1].astype(np.int64)).to(device),
+                'window': torch.from_numpy(log2_window_table()).to(device),
+            }
+            hc = HllConsts()
+            hc.p = self.p
+            hc.table_len = est.numel()
+            hc.monotone = int(bool(torch.all(est[1:] >= est[:-1])))
+            hc.threshold = float(np.float32(self.hll_threshold))
+            hc.alpha_m2 = float(np.float32(self.alpha * self.m ** 2))
+            hc.five_m = float(np.float32(5 * self.m))
+            hc.lc_table = d['lc'].data_ptr()
+            hc.raw_estimate = d['est'].data_ptr()
+            hc.bias = d['bias'].data_ptr()
+            d['hc'] = hc
+            self._dev[key] = d
+        return d
+
+    def _record_bytes(self):
+        return check(lib.ss_record_bytes(self.num_perm, self.p), 'ss_record_bytes')
+
+    # ------------------------------------------------------------------ host helpers (numpy, as the reference)
+    def _np_bit_length(self, bits):
+        """bits needed to represent each int, evaluated like the reference in float64 (hashing.py:83-89)"""
+        return np.ceil(np.log2(bits + 1)).astype(int)
+
+    def _get_hll_rank(self, bits):
+        """leading-zero rank of each value in a max_rank-bit word (hashing.py:91-104)"""
+        bit_length = self._np_bit_length(bits)
+        rank = self.max_rank - bit_length + 1
+        if min(rank) <= 0:
+            raise ValueError("Hash value overflow, maximum size is %d\
+                        bits" % self.max_rank)
+        return rank
+
+    def _init_permutations(self, num_perm):
+        """(a, b) of the affine permutations; legacy RandomState stream, a then b per permutation
+        (hashing.py:106-116) -> uint64 [2, num_perm]"""
+        gen = np.random.RandomState(self.minhash_seed)
+        ab = np.empty((2, num_perm), dtype=np.uint64)
+        for j in range(num_perm):
+            ab[0, j] = gen.randint(1, self._mersenne_prime, dtype=np.uint64)
+            ab[1, j] = gen.randint(0, self._mersenne_prime, dtype=np.uint64)
+        return ab
+
+    # ------------------------------------------------------------------ K1
+    def _init_records(self, n_nodes, device, first_id=1, out=None):
+        d = self._consts(device)
+        rb = self._record_bytes()
+        rec = out if out is not None else torch.empty((n_nodes, rb), dtype=torch.uint8, device=device)
+        check(lib.ss_init_records(n_nodes, first_id, self.num_perm, self.p, _ptr(d['perm_a']), _ptr(d['perm_b']),
+                                  _ptr(d['window']), _ptr(rec), rec.stride(0) if n_nodes else rb,
+                                  _stream_ptr(device)), 'ss_init_records')
+        return rec
+
+    def initialise_minhash(self, n_nodes):
+        """hop-0 MinHash signatures, int64 [n, P] on the CPU like the reference (hashing.py:118-124)"""
+        device = _cuda_device()
+        with torch.cuda.device(device):
+            rec = self._init_records(n_nodes, device)
+            return HopSketch(rec, self.num_perm, self.p, torch.device('cpu'))['minhash']
+
+    def initialise_hll(self, n_nodes):
+        """hop-0 HLL registers, int8 [n, m] on the CPU like the reference (hashing.py:126-137)"""
+        device = _cuda_device()
+        with torch.cuda.device(device):
+            rec = self._init_records(n_nodes, device)
+            return HopSketch(rec, self.num_perm, self.p, torch.device('cpu'))['hll']
+
+    # ------------------------------------------------------------------ K2
+    def _merge(self, rowptr, colidx, nnz, rec_in, rec_out, cards_col, device, ws=None):
+        d = self._consts(device)
+        n_rows = rec_out.shape[0]
+        need = check(lib.ss_merge_workspace_bytes(nnz, self.num_perm, self.p), 'ss_merge_workspace_bytes')
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
+        check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.stride(0),
+                                _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p, _ptr(ws), ws.numel(),
+                                _ptr(cards_col), cards_col.stride(0) if cards_col is not None else 0,
+                                ctypes.byref(d['hc']), _lib.MERGE_VARIANTS[self.merge_variant],
+                                _stream_ptr(device)), 'ss_khop_merge')
+        return ws
+
+    def build_hash_tables(self, num_nodes, edge_index):
+        """
+        Generate a hashing table that allows the size of the intersection of two nodes k-hop neighbours to be
+        estimated in constant time (hashing.py:139-165)
+        @param num_nodes: The number of nodes in the graph
+        @param edge_index: Int Tensor [2, edges] edges in the graph
+        @return: hashes, cards. Hashes is a mapping {hop: {'hll', 'minhash'}}, cards is a tensor
+        [n_nodes, max_hops] on edge_index.device
+        """
+        device = _cuda_device(edge_index)
+        out_device = edge_index.device
+        with torch.cuda.device(device):
+            start = time()
+            rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=num_nodes, add_loops=True)
+            if max_id >= num_nodes:
+                raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
+            rb = self._record_bytes()
+            cards = torch.zeros((num_nodes, self.max_hops), dtype=torch.float32, device=device)
+            recs = [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(self.max_hops + 1)]
+            ws = None
+            for k in range(self.max_hops + 1):
+                logger.info(f"Calculating hop {k} hashes")
+                if k == 0:
+                    self._init_records(num_nodes, device, out=recs[0])
+                elif num_nodes > 0:
+                    ws = self._merge(rowptr, colidx, nnz, recs[k - 1], recs[k], cards[:, k - 1], device, ws)
+            logger.info(f'hash generation enqueued in {time() - start} s')
+            tables = SketchTables({k: HopSketch(recs[k], self.num_perm, self.p, out_device)
+                                   for k in range(self.max_hops + 1)}, self.num_perm, self.p)
+            return tables, cards.to(out_device)
+
+    # ------------------------------------------------------------------ K4
+    def _hop_views(self, hash_table, device):
+        """HopView[K+1] over compact records; packs reference-layout tensors on the fly"""
+        views = (HopView * (self.max_hops + 1))()
+        keep = []
+        rb = self._record_bytes()
+        for k in range(1, self.max_hops + 1):
+            entry = dict.__getitem__(hash_table, k) if isinstance(hash_table, SketchTables) else hash_table[k]
+            if isinstance(entry, HopSketch) and entry.records.device == device:
+                rec = entry.records
+            else:
+                mh = _to_device(entry['minhash'], device)
+                hl = _to_device(entry['hll'], device)
+                mh = (mh if mh.dtype == torch.int64 else mh.long()).contiguous()
+                hl = (hl if hl.dtype == torch.int8 else hl.to(torch.int8)).contiguous()
+                if mh.shape[1] != self.num_perm or hl.shape[1] != self.m or mh.shape[0] != hl.shape[0]:
+                    raise ValueError('hash table shapes do not match num_perm / hll_p of this ElphHashes')
+                rec = torch.empty((mh.shape[0], rb), dtype=torch.uint8, device=device)
+                check(lib.ss_pack_records(_ptr(mh), _ptr(hl), mh.shape[0], self.num_perm, self.p, _ptr(rec),
+                                          rec.stride(0), _stream_ptr(device)), 'ss_pack_records')
+            keep.append(rec)
+            views[k].records = rec.data_ptr()
+            views[k].row_stride = rec.stride(0)
+        return views, keep
+
+    def _link_kernel(self, links, views, cards, device, want_features, want_inter):
+        d = self._consts(device)
+        n = links.shape[0]
+        K = self.max_hops
+        feats = torch.empty((n, K * (K + 2)), dtype=torch.float32, device=device) if want_features else None
+        inter = torch.empty((n, K * K), dtype=torch.float32, device=device) if want_inter else None
+        flags = (_lib.SS_FLAG_USE_ZERO_ONE if self.use_zero_one else 0) | (_lib.SS_FLAG_FLOOR if self.floor_sf else 0)
+        check(lib.ss_link_features(_ptr(links), n, views, K, self.num_perm, self.p, _ptr(cards),
+                                   cards.stride(0) if cards is not None else 0, ctypes.byref(d['hc']), flags,
+                                   _ptr(feats), _ptr(inter), _stream_ptr(device)), 'ss_link_features')
+        return feats, inter
+
+    def _check_links(self, links, hash_table, device):
+        if self.max_hops not in (1, 2, 3):
+            raise NotImplementedError("Only 1, 2 and 3 hop hashes are implemented")
+        ld = _to_device(links, device)
+        ld = (ld if ld.dtype == torch.int64 else ld.long()).contiguous()
+        if ld.dim() != 2 or ld.shape[1] != 2:
+            raise ValueError('links must be [n_edges, 2]')
+        if self.validate_links and ld.numel():
+            entry = dict.__getitem__(hash_table, 1) if isinstance(hash_table, SketchTables) else hash_table[1]
+            n_nodes = entry.records.shape[0] if isinstance(entry, HopSketch) else entry['hll'].shape[0]
+            lo, hi = int(ld.min()), int(ld.max())
+            if lo < 0 or hi >= n_nodes:
+                raise IndexError(f'link endpoint out of range [0, {n_nodes}): min {lo}, max {hi}')
+        return ld
+
+    def _get_intersections(self, edge_list, hash_table):
+        """
+        extract set intersections as jaccard * union (hashing.py:167-189)
+        @param edge_list: [n_edges, 2] tensor to get intersections for
+        @return: {(k1, k2): float32 [n_edges]} for k1, k2 in 1..max_hops
+        """
+        device = _cuda_device(edge_list)
+        with torch.cuda.device(device):
+            ld = self._check_links(edge_list, hash_table, device)
+            views, keep = self._hop_views(hash_table, device)
+            _, inter = self._link_kernel(ld, views, None, device, False, True)
+            inter = inter.to(edge_list.device)
+            K = self.max_hops
+            return {(k1, k2): inter[:, (k1 - 1) * K + (k2 - 1)] for k1 in range(1, K + 1) for k2 in range(1, K + 1)}
+
+    def get_subgraph_features(self, links, hash_table, cards, batch_size=11000000):
+        """
+        structural features of each link: hop-wise intersection / difference cardinalities
+        (hashing.py:258-323)
+        @param links: tensor [n_edges, 2]
+        @param hash_table: mapping {hop: {'hll', 'minhash'}} (a SketchTables or the reference's dict of tensors)
+        @param cards: Tensor[n_nodes, max_hops] of hll neighbourhood cardinality estimates
+        @param batch_size: links per kernel launch; the result does not depend on it
+        @return: Tensor[n_edges, max_hops(max_hops+2)] on links.device
+        """
+        if links.dim() == 1:
+            links = links.unsqueeze(0)
+        device = _cuda_device(links)
+        K = self.max_hops
+        with torch.cuda.device(device):
+            views, keep = self._hop_views(hash_table, device)
+            cd = _to_device(cards, device)
+            cd = (cd if cd.dtype == torch.float32 else cd.float()).contiguous()
+            if cd.dim() != 2 or cd.shape[1] < K:
+                raise ValueError('cards must be [n_nodes, max_hops]')
+            ld = self._check_links(links, hash_table, device)
+            n = ld.shape[0]
+            out = torch.empty((n, K * (K + 2)), dtype=torch.float32, device=device)
+            batch_size = max(int(batch_size), 1)
+            d = self._consts(device)
+            flags = (_lib.SS_FLAG_USE_ZERO_ONE if self.use_zero_one else 0) | \
+                    (_lib.SS_FLAG_FLOOR if self.floor_sf else 0)
+            for lo in range(0, n, batch_size):
+                hi = min(lo + batch_size, n)
+                check(lib.ss_link_features(_ptr(ld[lo:hi]), hi - lo, views, K, self.num_perm, self.p, _ptr(cd),
+                                           cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out[lo:hi]), None,
+                                           _stream_ptr(device)), 'ss_link_features')
+            return out if links.device == device else out.to(links.device)
+
+    # ------------------------------------------------------------------ K3 / K5 helpers
+    def get_hashval(self, x):
+        return x.hashvals
+
+    def _linearcounting(self, num_zero):
+        """m * log(m / num_zero) (hashing.py:194-195) via the table built with that expression"""
+        return self._lc_host.to(num_zero.device)[num_zero.long()]
+
+    def _estimate_bias(self, e):
+        """mean bias of the 6 nearest raw estimates (hashing.py:197-204)"""
+        device = _cuda_device(e)
+        with torch.cuda.device(device):
+            d = self._consts(device)
+            ed = _to_device(e, device).float().contiguous()
+            out = torch.empty_like(ed)
+            check(lib.ss_estimate_bias(_ptr(ed), ed.numel(), ctypes.byref(d['hc']), _ptr(out), _stream_ptr(device)),
+                  'ss_estimate_bias')
+            return out.to(e.device)
+
+    def _refine_hll_count_estimate(self, estimate):
+        """subtract the bias where estimate <= 5m, in place like the reference (hashing.py:206-210)"""
+        idx = estimate <= 5 * self.m
+        estimate_bias = self._estimate_bias(estimate)
+        estimate[idx] = estimate[idx] - estimate_bias[idx]
+        return estimate
+
+    def hll_count(self, regs):
+        """
+        Estimate the size of set unions associated with regs (hashing.py:212-232)
+        @param regs: A tensor of registers [n_nodes, register_size] (or one row)
+        @return: float32 [n_nodes] on regs.device
+        """
+        if regs.dim() == 1:
+            regs = regs.unsqueeze(dim=0)
+        if regs.shape[1] != self.m:
+            raise ValueError(f'register rows must have {self.m} entries')
+        device = _cuda_device(regs)
+        with torch.cuda.device(device):
+            d = self._consts(device)
+            rd = _to_device(regs, device)
+            rd = (rd if rd.dtype in (torch.int8, torch.uint8) else rd.to(torch.uint8)).contiguous()
+            out = torch.empty(rd.shape[0], dtype=torch.float32, device=device)
+            check(lib.ss_hll_count(_ptr(rd), rd.stride(0) if rd.shape[0] else self.m, rd.shape[0],
+                                   ctypes.byref(d['hc']), _ptr(out), 1, _stream_ptr(device)), 'ss_hll_count')
+            return out.to(regs.device)
+
+    def _hll_merge(self, src, dst):
+        if src.shape != dst.shape:
+            raise ValueError('source and destination register shapes must be the same')
+        device = _cuda_device(src)
+        with torch.cuda.device(device):
+            a = _to_device(src, device).to(torch.int8).contiguous()
+            b = _to_device(dst, device).to(torch.int8).contiguous()
+            out = torch.empty_like(a)
+            check(lib.ss_max_i8(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream_ptr(device)), 'ss_max_i8')
+            return out.to(src.dtype).to(src.device)
+
+    def _neighbour_merge(self, root, neighbours, is_min):
+        device = _cuda_device(root)
+        with torch.cuda.device(device):
+            want = torch.int64 if is_min else torch.int8
+            rows = torch.cat([_to_device(root, device).unsqueeze(dim=0), _to_device(neighbours, device)], dim=0)
+            rows = rows.to(want).contiguous()
+            rowptr = torch.tensor([0, rows.shape[0]], dtype=torch.int64, device=device)
+            out = torch.empty((1, rows.shape[1]), dtype=want, device=device)
+            fn = lib.ss_prop_min_i64 if is_min else lib.ss_prop_max_i8
+            check(fn(_ptr(rowptr), None, 1, _ptr(rows), _ptr(out), rows.shape[1], _stream_ptr(device)), 'ss_prop')
+            return out[0].to(root.dtype).to(root.device)
+
+    def hll_neighbour_merge(self, root, neighbours):
+        return self._neighbour_merge(root, neighbours, is_min=False)
+
+    def minhash_neighbour_merge(self, root, neighbours):
+        return self._neighbour_merge(root, neighbours, is_min=True)
+
+    def jaccard(self, src, dst):
+        """
+        get the minhash Jaccard estimate (hashing.py:247-256)
+        @param src: tensor [n_edges, num_perms] of hashvalues
+        @param dst: tensor [n_edges, num_perms] of hashvalues
+        @return: tensor [n_edges] jaccard estimates
+        """
+        if src.shape != dst.shape:
+            raise ValueError('source and destination hash value shapes must be the same')
+        device = _cuda_device(src)
+        with torch.cuda.device(device):
+            width = src.shape[-1]
+            a = _to_device(src, device).long().reshape(-1, width).contiguous()
+            b = _to_device(dst, device).long().reshape(-1, width).contiguous()
+            out = torch.empty(a.shape[0], dtype=torch.float32, device=device)
+            # the reference divides by num_perm whatever the row width (hashing.py:256)
+            check(lib.ss_jaccard_i64(_ptr(a), _ptr(b), a.shape[0], width, self.num_perm, _ptr(out),
+                                     _stream_ptr(device)), 'ss_jaccard_i64')
+            return out.reshape(src.shape[:-1]).to(src.device)

@@ -1,0 +1,118 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/ss_b200.h declares; host-side logic of
+the ElphHashes mirror (constants, permutations, error behaviour).  No compute call is made without a GPU."""
+import os
+import re
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+import subgraph_sketching_b200 as ssb
+from subgraph_sketching_b200 import _lib
+from helpers import make_args
+from oracle import sketch_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'ss_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(ss_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(_lib.lib, s), f'{s} declared in ss_b200.h but not exported by libss_b200.so'
+        assert s in _lib.SIGNATURES, f'{s} has no ctypes signature in _lib.py'
+    assert sorted(_lib.SIGNATURES) == syms
+    assert _lib.lib.ss_version() == _lib.SS_ABI_VERSION
+
+
+def test_record_geometry_and_argument_errors():
+    assert _lib.lib.ss_record_bytes(128, 8) == 768
+    assert _lib.lib.ss_record_bytes(33, 6) == 4 * 36 + 64
+    assert _lib.lib.ss_record_bytes(8, 4) == 48
+    assert _lib.lib.ss_record_bytes(128, 3) < 0
+    assert b'unsupported' in _lib.lib.ss_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib.ss_record_bytes(0, 8), 'ss_record_bytes')
+    assert _lib.lib.ss_csr_workspace_bytes(1000) >= 4000
+    assert _lib.lib.ss_merge_workspace_bytes(10, 33, 6) == 16
+
+
+def test_constructor_mirrors_reference():
+    for bad in (0, 4):
+        with pytest.raises(AssertionError):
+            ssb.ElphHashes(make_args(K=bad))
+    eh = ssb.ElphHashes(make_args(K=3, use_zero_one=True))
+    assert eh.max_hops == 3 and eh.num_perm == 128 and eh.p == 8 and eh.m == 256
+    assert eh.max_rank == 56 and eh.hll_size == 256 and eh.use_zero_one is True and eh.floor_sf is False
+    assert eh.label_lookup == ssb.LABEL_LOOKUP[3]
+    assert [len(ssb.LABEL_LOOKUP[k]) for k in (1, 2, 3)] == [3, 8, 15]
+    assert abs(eh.alpha - 0.7182725932495458) < 1e-15
+    assert eh.hll_threshold == 220
+    assert eh.estimate_vector.dtype == torch.float32 and eh.bias_vector.shape == eh.estimate_vector.shape
+    assert int(eh._max_minhash) == 2 ** 32 - 1 and int(eh._mersenne_prime) == 2 ** 61 - 1
+    assert callable(eh.minhash_prop) and callable(eh.hll_prop)
+
+
+def test_host_helpers_match_oracle():
+    eh = ssb.ElphHashes(make_args())
+    ab = eh._init_permutations(128)
+    a, b = so.permutation_params(128)
+    assert ab.dtype == np.uint64 and np.array_equal(ab[0], a) and np.array_equal(ab[1], b)
+    bits = np.arange(1000, dtype=np.uint64)
+    assert eh._np_bit_length(bits).tolist() == [int(i).bit_length() for i in range(1000)]
+    assert eh._get_hll_rank(np.array([1, 2, 3], dtype=np.uint64)).tolist() == [56, 55, 55]
+    with pytest.raises(ValueError):
+        eh._get_hll_rank(np.array([2 ** 57], dtype=np.uint64))
+    # linear-counting table == the reference expression evaluated by torch (hashing.py:195)
+    c = so.HllConstants(8)
+    nz = torch.arange(1, 257)
+    assert torch.equal(eh._linearcounting(nz), so.linear_counting(c, nz))
+
+
+def test_log2_window_reproduces_float64_bit_length():
+    w = ssb.log2_window_table()
+    assert w[:49].sum() == 0 and w[50] == 2
+    for k in (49, 50, 53, 56, 59):
+        base = 2 ** k
+        for j in (0, 1, int(w[k]), int(w[k]) + 1, 2 * int(w[k]) + 3):
+            want = int(so.bit_length_f64(np.array([base + j - 1], dtype=np.uint64))[0])
+            excess = j
+            got = k if (excess == 0 or excess <= w[k]) else k + 1
+            assert got == want, (k, j)
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    eh = ssb.ElphHashes(make_args())
+    with pytest.raises(_lib.SketchLibError):
+        eh.build_hash_tables(4, torch.tensor([[0, 1], [1, 0]]))
+    with pytest.raises(_lib.SketchLibError):
+        eh.hll_count(torch.zeros(256, dtype=torch.int8))
+    with pytest.raises(_lib.SketchLibError):
+        eh.initialise_minhash(3)
+
+
+def test_shape_errors_precede_device_work():
+    eh = ssb.ElphHashes(make_args())
+    with pytest.raises(ValueError):
+        eh.jaccard(torch.zeros(3, 128), torch.zeros(4, 128))
+    with pytest.raises(ValueError):
+        eh._hll_merge(torch.zeros(3, 256), torch.zeros(3, 255))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'subgraph_sketching_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                assert '/root/reference' not in text.replace('/root/reference/src', 'REFDOC'), f

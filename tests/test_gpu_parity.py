@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA engine (through the ctypes C ABI) against the golden vectors of the
+unmodified reference and against the CPU oracle on seeded inputs.  Integer sketches must be bit-exact;
+floats within 1e-6 of the magnitude involved (helpers.float_close)."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import subgraph_sketching_b200 as ssb
+from helpers import (GRAPH_CASES, float_close, golden_tables, link_scale, load_golden, make_args, rmat_edges)
+from oracle import sketch_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def engine_for(blob, use_zero_one=False, floor_sf=False, variant='auto'):
+    args = make_args(int(blob['K']), int(blob['P']), int(blob['p']), use_zero_one, floor_sf)
+    return ssb.ElphHashes(args, hll_tables=golden_tables(blob), merge_variant=variant)
+
+
+def variants_for(blob):
+    return ['auto', 'tma', 'ldg', 'generic'] if (int(blob['P']), int(blob['p'])) == (128, 8) else ['auto']
+
+
+@pytest.mark.parametrize('name', GRAPH_CASES)
+def test_tables_bit_exact_vs_reference_golden(name):
+    blob = load_golden(name)
+    ei = torch.from_numpy(blob['edge_index']).to(DEV)
+    n, K = int(blob['num_nodes']), int(blob['K'])
+    for variant in variants_for(blob):
+        eh = engine_for(blob, variant=variant)
+        tables, cards = eh.build_hash_tables(n, ei)
+        assert len(tables) == K + 1 and cards.shape == (n, K) and cards.is_cuda
+        for k in range(K + 1):
+            mh = tables[k]['minhash']
+            hl = tables[k]['hll']
+            assert mh.dtype == torch.int64 and hl.dtype == torch.int8 and mh.is_cuda
+            assert np.array_equal(mh.cpu().numpy().astype(np.uint32), blob[f'minhash_{k}']), (variant, k)
+            assert np.array_equal(hl.cpu().numpy(), blob[f'hll_{k}']), (variant, k)
+        ok, err = float_close(cards.cpu(), blob['cards'], torch.from_numpy(blob['cards']))
+        assert ok, (variant, err)
+
+
+@pytest.mark.parametrize('name', GRAPH_CASES)
+def test_features_vs_reference_golden(name):
+    blob = load_golden(name)
+    ei = torch.from_numpy(blob['edge_index']).to(DEV)
+    links = torch.from_numpy(blob['links']).to(DEV)
+    n, K = int(blob['num_nodes']), int(blob['K'])
+    scale = link_scale(blob['links'], blob['cards'])
+    eh = engine_for(blob)
+    tables, cards = eh.build_hash_tables(n, ei)
+    for zo in (False, True):
+        for fl in (False, True):
+            eh.use_zero_one, eh.floor_sf = zo, fl
+            f = eh.get_subgraph_features(links, tables, cards)
+            assert f.shape == (links.shape[0], K * (K + 2)) and f.dtype == torch.float32 and f.is_cuda
+            ok, err = float_close(f.cpu(), blob[f'features_zo{int(zo)}_fl{int(fl)}'], scale)
+            assert ok, (zo, fl, err)
+    inter = eh._get_intersections(links, tables)
+    assert len(inter) == K * K
+    got = torch.stack([inter[(a, b)] for a in range(1, K + 1) for b in range(1, K + 1)], dim=1)
+    ok, err = float_close(got.cpu(), blob['intersections'], scale)
+    assert ok, err
+    # the reference's own dict-of-tensors layout (e.g. a table loaded from a hashcache.pt) gives the same
+    plain = {k: {'minhash': torch.from_numpy(blob[f'minhash_{k}'].astype(np.int64)),
+                 'hll': torch.from_numpy(blob[f'hll_{k}'])} for k in range(K + 1)}
+    eh.use_zero_one, eh.floor_sf = True, False
+    f_plain = eh.get_subgraph_features(links.cpu(), plain, torch.from_numpy(blob['cards']))
+    assert not f_plain.is_cuda
+    ok, err = float_close(f_plain, blob['features_zo1_fl0'], scale)
+    assert ok, err
+
+
+def test_hll_count_and_bias_golden():
+    blob = load_golden('hll_count_p8')
+    eh = ssb.ElphHashes(make_args(), hll_tables=golden_tables(blob))
+    regs = torch.from_numpy(blob['regs'])
+    for r in (regs, regs.to(DEV), regs.long(), regs.to(DEV).int()):
+        got = eh.hll_count(r)
+        assert got.device == r.device and got.dtype == torch.float32
+        ok, err = float_close(got.cpu(), blob['counts'], torch.from_numpy(blob['counts']))
+        assert ok, err
+    assert eh.hll_count(regs[3]).shape == (1,)
+    # known answers from the survey (table independent)
+    assert abs(float(eh.hll_count(torch.full((256,), 3, dtype=torch.int8))) - 1471.022216797) < 2e-3
+    # LC regime is bit-exact (table built with the reference expression)
+    lc_rows = blob['counts'] <= 220
+    assert np.array_equal(eh.hll_count(regs).numpy()[lc_rows], blob['counts'][lc_rows])
+    bias = eh._estimate_bias(torch.from_numpy(blob['e']))
+    flips = np.abs(bias.numpy() - blob['bias']) > 1e-5 * np.maximum(1.0, np.abs(blob['bias']))
+    assert flips.mean() <= 0.01, f'{flips.sum()} 6-NN neighbour-set flips out of {flips.size}'
+    # estimates above 5m are untouched by the refinement (test_hashing.py:229-236)
+    e = torch.tensor([5 * 256 + 1.0, 4000.0, 1e6])
+    assert torch.equal(eh._refine_hll_count_estimate(e.clone()), e)
+    small = torch.tensor([300.0, 800.0])
+    assert not torch.equal(eh._refine_hll_count_estimate(small.clone()), small)
+
+
+@pytest.mark.parametrize('K,seed', [(2, 0), (3, 1)])
+def test_rmat_with_hubs_vs_oracle(K, seed):
+    """power-law graph: hub rows span many ranges of the nnz-split merge; every variant must be bit-exact"""
+    scale = 12
+    n = 1 << scale
+    ei = rmat_edges(scale, 16, seed)
+    g = torch.Generator().manual_seed(seed)
+    links = torch.cat([torch.randint(0, n, (3000, 2), generator=g), ei[:, :3000].t()])
+    o = so.OracleSketches(K, 128, 8, use_zero_one=False, floor_sf=False)
+    ot, oc = o.build_hash_tables(n, ei)
+    of = o.subgraph_features(links, ot, oc)
+    deg = torch.bincount(ei[1], minlength=n)
+    assert int(deg.max()) > 512  # a real hub
+    for variant in ('tma', 'ldg', 'generic'):
+        eh = ssb.ElphHashes(make_args(K), merge_variant=variant)
+        tables, cards = eh.build_hash_tables(n, ei.to(DEV))
+        for k in range(K + 1):
+            assert torch.equal(tables[k]['minhash'].cpu(), ot[k]['minhash']), (variant, k)
+            assert torch.equal(tables[k]['hll'].cpu(), ot[k]['hll']), (variant, k)
+        ok, err = float_close(cards.cpu(), oc, oc)
+        assert ok, (variant, err)
+    f = eh.get_subgraph_features(links.to(DEV), tables, cards)
+    ok, err = float_close(f.cpu(), of, link_scale(links, oc))
+    assert ok, err
+
+
+def test_init_invariants_and_known_answers():
+    """ports of test_initialise_hll / test_initialise_minhash (test/test_hashing.py:338-353) + survey goldens"""
+    eh = ssb.ElphHashes(make_args())
+    n = 1000
+    hll = eh.initialise_hll(n)
+    mh = eh.initialise_minhash(n)
+    assert not hll.is_cuda and hll.dtype == torch.int8 and hll.shape == (n, 256)
+    assert not mh.is_cuda and mh.dtype == torch.int64 and mh.shape == (n, 128)
+    assert torch.equal(torch.count_nonzero(hll, dim=1), torch.ones(n, dtype=torch.long))
+    assert int(hll.min()) >= 0 and int(hll.max()) <= eh.max_rank + 1
+    assert int(mh.max()) <= 2 ** 32 - 1 and int(mh.min()) >= 0
+    assert mh[0, :4].tolist() == [4183491429, 1571535613, 1357840683, 3557095531]
+    assert mh[1, :4].tolist() == [1090388868, 3382136556, 2349435535, 3020319954]
+    got = [(int(torch.nonzero(r)[0]), int(r.max())) for r in hll[:5]]
+    assert got == [(229, 2), (138, 1), (240, 4), (20, 1), (220, 1)]
+    assert np.array_equal(mh.numpy(), so.minhash_init(n, 128))
+    assert np.array_equal(hll.numpy(), so.hll_init(n, 8))
+    counts = eh.hll_count(hll)
+    assert torch.all((counts - 1).abs() < 0.1)
+    for P, p in ((8, 4), (33, 6), (64, 10), (16, 14)):
+        e2 = ssb.ElphHashes(make_args(P=P, p=p))
+        assert np.array_equal(e2.initialise_minhash(77).numpy(), so.minhash_init(77, P))
+        assert np.array_equal(e2.initialise_hll(77).numpy(), so.hll_init(77, p))
+
+
+def test_init_large_ids_match_oracle_slice():
+    """ids far from 0 (sharded init uses first_id = 1 + row offset)"""
+    eh = ssb.ElphHashes(make_args())
+    dev = torch.device(DEV)
+    first = 16_000_000
+    rec = eh._init_records(4096, dev, first_id=first)
+    hop = ssb.HopSketch(rec, 128, 8, torch.device('cpu'))
+    assert np.array_equal(hop['minhash'].numpy(), so.minhash_init(4096, 128, first_id=first))
+    assert np.array_equal(hop['hll'].numpy(), so.hll_init(4096, 8, first_id=first))
+
+
+def test_propagate_operators_two_node_graph():
+    """port of test_propagate_minhash (test/test_hashing.py:355-385)"""
+    eh = ssb.ElphHashes(make_args())
+    ei = torch.tensor([[0, 1, 0, 1], [1, 0, 0, 1]], device=DEV)
+    mh = eh.initialise_minhash(2).to(DEV)
+    hl = eh.initialise_hll(2).to(DEV)
+    out = eh.minhash_prop(mh, ei)
+    assert out.dtype == torch.int64 and out.is_cuda
+    want = torch.min(mh, dim=0).values
+    assert torch.equal(out[0], want) and torch.equal(out[1], want)
+    out = eh.hll_prop(hl, ei)
+    want = torch.max(hl, dim=0).values
+    assert out.dtype == torch.int8 and torch.equal(out[0], want) and torch.equal(out[1], want)
+    # CPU tensors are offloaded transparently and come back on the CPU
+    out_cpu = eh.minhash_prop(mh.cpu(), ei.cpu())
+    assert not out_cpu.is_cuda and torch.equal(out_cpu, eh.minhash_prop(mh, ei).cpu())
+
+
+def test_propagate_operators_vs_oracle_and_tables():
+    n = 700
+    g = torch.Generator().manual_seed(9)
+    ei = torch.randint(0, 600, (2, 5000), generator=g)  # nodes 600.. have no edges
+    ei_loops = so.with_self_loops(ei)
+    eh = ssb.ElphHashes(make_args(K=2))
+    mh0 = eh.initialise_minhash(n)
+    hl0 = eh.initialise_hll(n)
+    mh1 = eh.minhash_prop(mh0.to(DEV), ei_loops.to(DEV))
+    hl1 = eh.hll_prop(hl0.to(DEV), ei_loops.to(DEV))
+    assert torch.equal(mh1.cpu(), so.minhash_propagate(mh0, ei_loops))
+    assert torch.equal(hl1.cpu(), so.hll_propagate(hl0, ei_loops))
+    assert int(mh1[650].abs().sum()) == 0 and int(hl1[650].abs().sum()) == 0  # no in-edge -> zeros (8a-Q4)
+    tables, cards = eh.build_hash_tables(n, ei.to(DEV))
+    assert torch.equal(tables[1]['minhash'], mh1) and torch.equal(tables[1]['hll'], hl1)
+    # test_hll_counts (test/test_hashing.py:216-227): cards[:, k] == hll_count(table[k+1].hll)
+    for k in range(2):
+        assert torch.allclose(cards[:, k], eh.hll_count(tables[k + 1]['hll']), atol=1e-8, rtol=0)
+        assert torch.allclose(cards[:, k], eh.hll_count(tables[k + 1]['hll'].long()), atol=1e-8, rtol=0)
+    assert float(cards[650].abs().sum()) == 0.0
+
+
+def test_neighbour_merge_port():
+    """port of test_neighbour_merge (test/test_hashing.py:313-329): hop-2 row == merge of hop-1 rows"""
+    blob = load_golden('ba30_k2')
+    ei = torch.from_numpy(blob['edge_index'])
+    eh = engine_for(blob)
+    tables, _ = eh.build_hash_tables(30, ei)
+    assert not tables[1]['hll'].is_cuda  # CPU edge_index -> CPU tables, like the reference
+    node = 5
+    nbrs = ei[0][ei[1] == node]
+    root_h, root_m = tables[1]['hll'][node], tables[1]['minhash'][node]
+    merged_h = eh.hll_neighbour_merge(root_h, tables[1]['hll'][nbrs])
+    merged_m = eh.minhash_neighbour_merge(root_m, tables[1]['minhash'][nbrs])
+    assert torch.equal(merged_h, tables[2]['hll'][node])
+    assert torch.equal(merged_m, tables[2]['minhash'][node])
+
+
+def test_small_helpers():
+    eh = ssb.ElphHashes(make_args())
+    g = torch.Generator().manual_seed(3)
+    a = torch.randint(0, 5, (50, 128), generator=g)
+    b = torch.randint(0, 5, (50, 128), generator=g)
+    want = torch.count_nonzero(a == b, dim=-1) / 128
+    assert torch.equal(eh.jaccard(a, b), want)
+    assert torch.equal(eh.jaccard(a.to(DEV), b.to(DEV)).cpu(), want)
+    assert float(eh.jaccard(a[0], a[0])) == 1.0 and eh.jaccard(a[0], b[0]).dim() == 0
+    h1 = torch.randint(0, 30, (40, 256), generator=g).to(torch.int8)
+    h2 = torch.randint(0, 30, (40, 256), generator=g).to(torch.int8)
+    assert torch.equal(eh._hll_merge(h1, h2), torch.maximum(h1, h2))
+    with pytest.raises(ValueError):
+        eh._hll_merge(h1, h2[:, :10])
+    with pytest.raises(ValueError):
+        eh.jaccard(a, b[:10])
+
+
+def test_feature_api_contract():
+    """ports of test_get_subgraph_features (test/test_hashing.py:179-194) and
+    test_get_subgraph_features_batched (test/test_elph_datasets.py:69-91)"""
+    blob = load_golden('ba300_k3')
+    for K in (1, 2, 3):
+        eh = ssb.ElphHashes(make_args(K, use_zero_one=True), hll_tables=golden_tables(blob))
+        ei = torch.from_numpy(blob['edge_index'])
+        links = torch.from_numpy(blob['links'])
+        tables, cards = eh.build_hash_tables(300, ei)
+        assert not cards.is_cuda
+        full = eh.get_subgraph_features(links, tables, cards)
+        assert not full.is_cuda and full.shape == (links.shape[0], K * (K + 2))
+        assert torch.equal(eh.get_subgraph_features(links, tables, cards, batch_size=3), full)
+        assert torch.equal(eh.get_subgraph_features(links, tables, cards, batch_size=7), full)
+        one = eh.get_subgraph_features(links[5], tables, cards)  # 1-D link
+        assert one.shape == (1, K * (K + 2)) and torch.equal(one[0], full[5])
+        eh.use_zero_one = False
+        ko = eh.get_subgraph_features(links, tables, cards)
+        want = full.clone()
+        for col in {1: [], 2: [4, 5], 3: [4, 5, 11, 12]}[K]:
+            want[:, col] = 0
+        assert torch.equal(ko, want)
+        eh.floor_sf = True
+        fl = eh.get_subgraph_features(links, tables, cards)
+        assert torch.equal(fl, torch.clamp(want, min=0) * 1.0) or torch.equal(fl, torch.where(want < 0, torch.zeros_like(want), want))
+        with pytest.raises(IndexError):
+            eh.get_subgraph_features(torch.tensor([[0, 300]]), tables, cards)
+
+
+def test_intersection_symmetry_and_self_links():
+    """size-independent property: I(k1,k2)(u,v) == I(k2,k1)(v,u), bit for bit"""
+    n = 1 << 14
+    ei = rmat_edges(14, 8, 7).to(DEV)
+    eh = ssb.ElphHashes(make_args(3))
+    tables, cards = eh.build_hash_tables(n, ei)
+    g = torch.Generator().manual_seed(1)
+    links = torch.randint(0, n, (50000, 2), generator=g).to(DEV)
+    a = eh._get_intersections(links, tables)
+    b = eh._get_intersections(links.flip(1), tables)
+    for k1 in (1, 2, 3):
+        for k2 in (1, 2, 3):
+            assert torch.equal(a[(k1, k2)], b[(k2, k1)])
+    # a self link (u,u): jaccard of hop k with itself is 1 -> I(k,k) == cards[u, k-1]
+    u = torch.arange(0, 2000, device=DEV)
+    s = eh._get_intersections(torch.stack([u, u], dim=1), tables)
+    for k in (1, 2, 3):
+        assert torch.equal(s[(k, k)], cards[u, k - 1])
+
+
+def test_tables_roundtrip_and_torch_save():
+    blob = load_golden('ba300_k3')
+    eh = engine_for(blob)
+    ei = torch.from_numpy(blob['edge_index']).to(DEV)
+    tables, cards = eh.build_hash_tables(300, ei)
+    buf = io.BytesIO()
+    torch.save(tables, buf)
+    buf.seek(0)
+    loaded = torch.load(buf)  # weights_only default: a plain mapping of CPU tensors
+    assert sorted(loaded.keys()) == [0, 1, 2, 3]
+    for k in range(4):
+        assert np.array_equal(loaded[k]['minhash'].numpy().astype(np.uint32), blob[f'minhash_{k}'])
+        assert np.array_equal(loaded[k]['hll'].numpy(), blob[f'hll_{k}'])
+    links = torch.from_numpy(blob['links']).to(DEV)
+    f1 = eh.get_subgraph_features(links, tables, cards)
+    f2 = eh.get_subgraph_features(links, loaded, cards)
+    assert torch.equal(f1, f2)
+
+
+def test_empty_and_degenerate_inputs():
+    eh = ssb.ElphHashes(make_args(2))
+    # no edges at all: add_self_loops adds nothing -> hop >= 1 rows are all zero
+    tables, cards = eh.build_hash_tables(5, torch.zeros((2, 0), dtype=torch.long, device=DEV))
+    assert int(tables[1]['minhash'].abs().sum()) == 0 and int(tables[2]['hll'].abs().sum()) == 0
+    assert float(cards.abs().sum()) == 0.0
+    assert int(tables[0]['hll'].count_nonzero()) == 5
+    f = eh.get_subgraph_features(torch.zeros((0, 2), dtype=torch.long, device=DEV), tables, cards)
+    assert f.shape == (0, 8)
+    # single self loop
+    tables, cards = eh.build_hash_tables(3, torch.tensor([[1], [1]], device=DEV))
+    assert torch.equal(tables[1]['minhash'][1], tables[0]['minhash'][1])
+    assert int(tables[1]['minhash'][2].abs().sum()) == 0
+    with pytest.raises(IndexError):
+        eh.build_hash_tables(3, torch.tensor([[0, 5], [1, 0]], device=DEV))
