@@ -70,6 +70,19 @@ def _to_device(t, device):
     return t.to(device, non_blocking=True)
 
 
+def _to_host(t):
+    """device -> pinned host copy (torch caches pinned blocks, so steady-state calls do not re-pin)"""
+    if not t.is_cuda:
+        return t
+    try:
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        return t.cpu()
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out
+
+
 def hllpp_tables(p):
     """(threshold, raw_estimate[T], bias[T]) for precision p: from `datasketch` when it is importable
     (what the reference reads, hashing.py:77-80), else from the packaged Monte-Carlo tables
@@ -316,6 +329,7 @@ class ElphHashes(object):
         self.hll_prop = HllPropagation()
         self.merge_variant = merge_variant
         self.validate_links = True  # bounds-check link endpoints (the reference raises IndexError)
+        self.event_log = None  # set to a list to record (name, start_event, end_event) around kernels
         # linear-counting table, evaluated with the reference's own float32 torch expression (hashing.py:195)
         nz = torch.arange(1, self.m + 1, dtype=torch.int64)
         self._lc_host = torch.cat([torch.zeros(1), self.m * torch.log(self.m / nz)]).float()
@@ -410,12 +424,28 @@ class ElphHashes(object):
         need = check(lib.ss_merge_workspace_bytes(nnz, self.num_perm, self.p), 'ss_merge_workspace_bytes')
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
+        ev = self._event_begin(device)
         check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.stride(0),
                                 _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p, _ptr(ws), ws.numel(),
                                 _ptr(cards_col), cards_col.stride(0) if cards_col is not None else 0,
                                 ctypes.byref(d['hc']), _lib.MERGE_VARIANTS[self.merge_variant],
                                 _stream_ptr(device)), 'ss_khop_merge')
+        self._event_end('khop_merge', ev, device)
         return ws
+
+    def _event_begin(self, device):
+        if self.event_log is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        return ev
+
+    def _event_end(self, name, start, device):
+        if start is None:
+            return
+        end = torch.cuda.Event(enable_timing=True)
+        end.record(torch.cuda.current_stream(device))
+        self.event_log.append((name, start, end))
 
     def build_hash_tables(self, num_nodes, edge_index):
         """
@@ -430,7 +460,9 @@ class ElphHashes(object):
         out_device = edge_index.device
         with torch.cuda.device(device):
             start = time()
+            ev = self._event_begin(device)
             rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=num_nodes, add_loops=True)
+            self._event_end('csr_build', ev, device)
             if max_id >= num_nodes:
                 raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
             rb = self._record_bytes()
@@ -440,13 +472,15 @@ class ElphHashes(object):
             for k in range(self.max_hops + 1):
                 logger.info(f"Calculating hop {k} hashes")
                 if k == 0:
+                    ev = self._event_begin(device)
                     self._init_records(num_nodes, device, out=recs[0])
+                    self._event_end('init_records', ev, device)
                 elif num_nodes > 0:
                     ws = self._merge(rowptr, colidx, nnz, recs[k - 1], recs[k], cards[:, k - 1], device, ws)
             logger.info(f'hash generation enqueued in {time() - start} s')
             tables = SketchTables({k: HopSketch(recs[k], self.num_perm, self.p, out_device)
                                    for k in range(self.max_hops + 1)}, self.num_perm, self.p)
-            return tables, cards.to(out_device)
+            return tables, (cards if out_device == device else _to_host(cards))
 
     # ------------------------------------------------------------------ K4
     def _hop_views(self, hash_table, device):
@@ -544,10 +578,12 @@ class ElphHashes(object):
                     (_lib.SS_FLAG_FLOOR if self.floor_sf else 0)
             for lo in range(0, n, batch_size):
                 hi = min(lo + batch_size, n)
+                ev = self._event_begin(device)
                 check(lib.ss_link_features(_ptr(ld[lo:hi]), hi - lo, views, K, self.num_perm, self.p, _ptr(cd),
                                            cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out[lo:hi]), None,
                                            _stream_ptr(device)), 'ss_link_features')
-            return out if links.device == device else out.to(links.device)
+                self._event_end('link_features', ev, device)
+            return out if links.device == device else _to_host(out)
 
     # ------------------------------------------------------------------ K3 / K5 helpers
     def get_hashval(self, x):

@@ -42,18 +42,6 @@ def link_scale(links, cards):
     return torch.maximum(cards[links[:, 0]].max(dim=1).values, cards[links[:, 1]].max(dim=1).values)
 
 
-def rmat_edges(scale, edge_factor, seed, device='cpu', a=0.57, b=0.19, c=0.19):
-    """Graph500-style R-MAT edge list, symmetrised and de-duplicated -> int64 [2, E]"""
-    n = 1 << scale
-    e = n * edge_factor
-    g = torch.Generator(device=device).manual_seed(seed)
-    src = torch.zeros(e, dtype=torch.int64, device=device)
-    dst = torch.zeros(e, dtype=torch.int64, device=device)
-    for _ in range(scale):
-        r = torch.rand(e, generator=g, device=device)
-        sb = (r >= a + b).long()
-        db = (((r >= a) & (r < a + b)) | (r >= a + b + c)).long()
-        src = src * 2 + sb
-        dst = dst * 2 + db
-    key = torch.unique(torch.cat([src * n + dst, dst * n + src]))
-    return torch.stack([key // n, key % n])
+def rmat_edges(scale, edge_factor, seed, device='cpu'):
+    from subgraph_sketching_b200.graphs import rmat_edges as gen
+    return gen(scale, edge_factor, seed, device)
