@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 2
+#define SS_ABI_VERSION 3
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -44,9 +44,10 @@ extern "C" {
 
 /* merge kernel variants (ss_khop_merge `variant`) */
 #define SS_MERGE_AUTO 0
-#define SS_MERGE_TMA 1          /* cp.async.bulk row staging through shared memory + mbarrier (P=128, p=8) */
+#define SS_MERGE_TMA 1          /* TMA row gather (cp.async.bulk.tensor tile::gather4) into a shared-memory ring (P=128, p=8) */
 #define SS_MERGE_LDG 2          /* direct 128-bit global loads, register accumulators (P=128, p=8) */
 #define SS_MERGE_GENERIC 3      /* any (P, p): column-chunk outer loop, no staging */
+#define SS_MERGE_BULK 4         /* one 1-D cp.async.bulk per row into the same ring (P=128, p=8) */
 
 typedef void *ss_stream_t;
 
@@ -127,7 +128,8 @@ int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t
  *   rec_out[r] = ( min over c in colidx[rowptr[r]..rowptr[r+1]) of rec_in[c].minhash,
  *                  max ...                                      of rec_in[c].hll )
  *   rows with no in-edge are all-zero (scatter-max fill).
- * rec_in is the full previous-hop table (indexed by global id), rec_out holds the n_rows owned rows
+ * rec_in is the full previous-hop table (in_rows records indexed by global id; every colidx entry must be
+ * < in_rows), rec_out holds the n_rows owned rows
  * (rowptr is local to them: rowptr[0] = 0, rowptr[n_rows] = nnz); rec_in and rec_out must not overlap.
  * cards_out[r * cards_stride] receives the float32 HLL++ estimate of row r (stride in elements).
  * workspace: ss_merge_workspace_bytes(nnz, P, p) bytes, 16-byte aligned.  The neighbour list is cut into
@@ -136,7 +138,7 @@ int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t
  */
 int64_t ss_merge_workspace_bytes(int64_t nnz, int num_perm, int hll_p);
 int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
-                  int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p, void *workspace,
+                  int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p, void *workspace,
                   int64_t workspace_bytes, float *cards_out, int64_t cards_stride, const ss_hll_consts *hc,
                   int variant, ss_stream_t stream);
 

@@ -10,11 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
 
-SS_ABI_VERSION = 2
+SS_ABI_VERSION = 3
 SS_FLAG_USE_ZERO_ONE = 1
 SS_FLAG_FLOOR = 2
-SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC = 0, 1, 2, 3
-MERGE_VARIANTS = {'auto': SS_MERGE_AUTO, 'tma': SS_MERGE_TMA, 'ldg': SS_MERGE_LDG, 'generic': SS_MERGE_GENERIC}
+SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC, SS_MERGE_BULK = 0, 1, 2, 3, 4
+MERGE_VARIANTS = {'auto': SS_MERGE_AUTO, 'tma': SS_MERGE_TMA, 'ldg': SS_MERGE_LDG, 'generic': SS_MERGE_GENERIC,
+                  'bulk': SS_MERGE_BULK}
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -46,7 +47,7 @@ SIGNATURES = {
     'ss_csr_rowptr': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_csr_fill': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_merge_workspace_bytes': (c_i64, [c_i64, c_int, c_int]),
-    'ss_khop_merge': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64,
+    'ss_khop_merge': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64,
                               c_ptr, c_i64, ctypes.POINTER(HllConsts), c_int, c_ptr]),
     'ss_prop_min_i64': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_prop_max_i8': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -21,6 +21,11 @@
 //        completion is tracked with one mbarrier per stage; the warp then reads the rows conflict-free.
 //   LDG: each lane issues LDG.128 + LDG.64 per neighbour row, U rows in flight in registers.
 // The generic kernel (any P, p) is row-per-warp with a column-chunk outer loop.
+#include <stdlib.h>
+#include <string.h>
+
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace ss {
@@ -75,56 +80,82 @@ __device__ __forceinline__ int64_t row_of_position(const int64_t *__restrict__ r
     return lo;
 }
 
-// state of the row currently being reduced by a warp
+// state of the row currently being reduced by a warp.  Positions are relative to the range start s
+// (32-bit: one compare per neighbour), clamped so that "started before" / "continues after" stay visible.
+// HLL registers are accumulated in two planes (even / odd bytes, each in its own 16-bit lane) so that the
+// register-wise max is the native 16x2 max (VIMNMX.U16x2 / VIMNMX3) -- a 4 x uint8 max does not exist in
+// hardware and costs 7 instructions when emulated.
 struct RowState {
     uint4 mh;
-    uint2 hl;
-    int64_t cur;      // row index
-    int64_t rs, re;   // its neighbour range [rs, re)
-    int64_t re_next;  // rowptr[cur + 2] (prefetched)
+    uint2 he, ho;   // even / odd byte planes of the 8 HLL registers of this lane
+    int cur;        // row index
+    int rs, re;     // neighbour range of the row relative to s: rs = -1 if it started before the range
+    int re_next;    // relative end of row cur + 1 (prefetched)
 };
+constexpr int REL_CAP = 1 << 30;
+constexpr uint32_t EVEN = 0x00ff00ffu, ODD = 0xff00ff00u;
 
+__device__ __forceinline__ int rel_pos(int64_t abs_pos, int64_t s) {
+    const int64_t d = abs_pos - s;
+    return d < 0 ? -1 : (d > REL_CAP ? REL_CAP : (int)d);
+}
 __device__ __forceinline__ void acc_reset(RowState &st) {
     st.mh = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    st.hl = make_uint2(0u, 0u);
+    st.he = make_uint2(0u, 0u);
+    st.ho = make_uint2(0u, 0u);
 }
 __device__ __forceinline__ void acc_merge(RowState &st, const uint4 &m, const uint2 &h) {
     st.mh.x = min(st.mh.x, m.x);
     st.mh.y = min(st.mh.y, m.y);
     st.mh.z = min(st.mh.z, m.z);
     st.mh.w = min(st.mh.w, m.w);
-    st.hl.x = __vmaxu4(st.hl.x, h.x);
-    st.hl.y = __vmaxu4(st.hl.y, h.y);
+    st.he.x = __vmaxu2(st.he.x, h.x & EVEN);
+    st.he.y = __vmaxu2(st.he.y, h.y & EVEN);
+    st.ho.x = __vmaxu2(st.ho.x, h.x & ODD);
+    st.ho.y = __vmaxu2(st.ho.y, h.y & ODD);
 }
+// two neighbour rows at once: three-input min / max (VIMNMX3)
+__device__ __forceinline__ void acc_merge2(RowState &st, const uint4 &m1, const uint2 &h1, const uint4 &m2,
+                                           const uint2 &h2) {
+    st.mh.x = __vimin3_u32(st.mh.x, m1.x, m2.x);
+    st.mh.y = __vimin3_u32(st.mh.y, m1.y, m2.y);
+    st.mh.z = __vimin3_u32(st.mh.z, m1.z, m2.z);
+    st.mh.w = __vimin3_u32(st.mh.w, m1.w, m2.w);
+    st.he.x = __vimax3_u16x2(st.he.x, h1.x & EVEN, h2.x & EVEN);
+    st.he.y = __vimax3_u16x2(st.he.y, h1.y & EVEN, h2.y & EVEN);
+    st.ho.x = __vimax3_u16x2(st.ho.x, h1.x & ODD, h2.x & ODD);
+    st.ho.y = __vimax3_u16x2(st.ho.y, h1.y & ODD, h2.y & ODD);
+}
+__device__ __forceinline__ uint2 acc_hll(const RowState &st) { return make_uint2(st.he.x | st.ho.x, st.he.y | st.ho.y); }
 
-// write the finished (or partial) current row; s/e = range bounds, w = range index
-__device__ __forceinline__ void flush_row(const MergeArgs &a, const RowState &st, int64_t w, int64_t s, int64_t e,
-                                          int lane) {
+// write the finished (or partial) current row; n_pos = length of the range, w = range index
+__device__ __forceinline__ void flush_row(const MergeArgs &a, const RowState &st, int64_t w, int n_pos, int lane) {
     if (st.rs == st.re) return;  // empty rows are zero-filled by the fix-up kernel
-    const bool whole = st.rs >= s && st.re <= e;
-    uint8_t *dst = whole ? a.out + st.cur * a.out_stride : a.scratch + (2 * w + (st.rs < s ? 0 : 1)) * (int64_t)REC;
+    const bool whole = st.rs >= 0 && st.re <= n_pos;
+    uint8_t *dst = whole ? a.out + (int64_t)st.cur * a.out_stride : a.scratch + (2 * w + (st.rs < 0 ? 0 : 1)) * (int64_t)REC;
+    const uint2 hl = acc_hll(st);
     st_na_u4(dst + lane * 16, st.mh);
-    st_na_u2(dst + REC_MH + lane * 8, st.hl);
+    st_na_u2(dst + REC_MH + lane * 8, hl);
     if (whole && a.cards) {
-        float c = ROW_CARD(a, st.hl);
-        if (lane == 0) a.cards[st.cur * a.cards_stride] = c;
+        float c = ROW_CARD(a, hl);
+        if (lane == 0) a.cards[(int64_t)st.cur * a.cards_stride] = c;
     }
 }
 
 // move to the next row (the one starting at st.re)
-__device__ __forceinline__ void advance_row(const MergeArgs &a, RowState &st) {
+__device__ __forceinline__ void advance_row(const MergeArgs &a, RowState &st, int64_t s) {
     st.cur += 1;
     st.rs = st.re;
     st.re = st.re_next;
-    st.re_next = (st.cur + 2 <= a.n_rows) ? __ldg(a.rowptr + st.cur + 2) : st.re;
+    st.re_next = ((int64_t)st.cur + 2 <= a.n_rows) ? rel_pos(__ldg(a.rowptr + st.cur + 2), s) : st.re;
     acc_reset(st);
 }
 
 __device__ __forceinline__ void begin_range(const MergeArgs &a, RowState &st, int64_t s) {
-    st.cur = row_of_position(a.rowptr, a.n_rows, s);
-    st.rs = __ldg(a.rowptr + st.cur);
-    st.re = __ldg(a.rowptr + st.cur + 1);
-    st.re_next = (st.cur + 2 <= a.n_rows) ? __ldg(a.rowptr + st.cur + 2) : st.re;
+    st.cur = (int)row_of_position(a.rowptr, a.n_rows, s);
+    st.rs = rel_pos(__ldg(a.rowptr + st.cur), s);  // rowptr[cur] <= s: 0 if the row starts here, else -1
+    st.re = rel_pos(__ldg(a.rowptr + st.cur + 1), s);
+    st.re_next = ((int64_t)st.cur + 2 <= a.n_rows) ? rel_pos(__ldg(a.rowptr + st.cur + 2), s) : st.re;
     acc_reset(st);
 }
 
@@ -139,15 +170,16 @@ __global__ void __launch_bounds__(256) merge_ldg_kernel(const MergeArgs a) {
     const uint8_t *__restrict__ in = a.in;
     for (int64_t w = gwarp; w < a.n_ranges; w += n_warps) {
         const int64_t s = w * a.quantum;
-        const int64_t e = min(s + (int64_t)a.quantum, a.nnz);
-        if (s >= e) continue;  // nnz == 0
+        const int n_pos = (int)min((int64_t)a.quantum, a.nnz - s);
+        if (n_pos <= 0) continue;  // nnz == 0
         RowState st;
         begin_range(a, st, s);
-        int32_t next_ids = (s + lane < e) ? __ldg(a.colidx + s + lane) : 0;
-        for (int64_t base = s; base < e; base += 32) {
+        const int32_t *__restrict__ ids_ptr = a.colidx + s;
+        int32_t next_ids = (lane < n_pos) ? __ldg(ids_ptr + lane) : 0;
+        for (int base = 0; base < n_pos; base += 32) {
             const int32_t ids = next_ids;
-            next_ids = (base + 32 + lane < e) ? __ldg(a.colidx + base + 32 + lane) : 0;
-            const int cnt = (int)min((int64_t)32, e - base);
+            next_ids = (base + 32 + lane < n_pos) ? __ldg(ids_ptr + base + 32 + lane) : 0;
+            const int cnt = min(32, n_pos - base);
             for (int j = 0; j < cnt; j += U) {
                 uint4 m[U];
                 uint2 h[U];
@@ -163,33 +195,88 @@ __global__ void __launch_bounds__(256) merge_ldg_kernel(const MergeArgs a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (j + u < cnt) {
-                        const int64_t pos = base + j + u;
+                        const int pos = base + j + u;
                         while (pos == st.re) {
-                            flush_row(a, st, w, s, e, lane);
-                            advance_row(a, st);
+                            flush_row(a, st, w, n_pos, lane);
+                            advance_row(a, st, s);
                         }
                         acc_merge(st, m[u], h[u]);
                     }
                 }
             }
         }
-        flush_row(a, st, w, s, e, lane);
+        flush_row(a, st, w, n_pos, lane);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA engine: per-warp ring of S stages x G rows, one mbarrier per stage
+// TMA engine: per-warp ring of S stages x 4 rows in shared memory, one mbarrier per stage.
+// Lane 0 is the producer: it reads the 4 neighbour ids of a group with one 16-byte load (prefetched one
+// group ahead), posts the expected byte count on the stage's mbarrier and issues
+//   GATHER4: ONE `cp.async.bulk.tensor.2d ... tile::gather4` (SASS UTMALDG) -- Blackwell's row-gather TMA:
+//            the 4 row indices go straight into the instruction, no address arithmetic; the previous-hop
+//            table is described by a 2-D tensor map [N rows x 192 uint32] built per call on the host;
+//   else   : four 1-D `cp.async.bulk` copies (SASS UBLKCP), one per row.
+// All 32 lanes then wait on the mbarrier and reduce the rows out of shared memory (conflict-free: lane l
+// reads bytes [16 l, 16 l + 16) of the MinHash part and [8 l, 8 l + 8) of the HLL part), two rows per step
+// where the output row does not change (three-input min/max).
 // ------------------------------------------------------------------------------------------------
-template <int G, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) merge_tma_kernel(const MergeArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ void mbar_init32(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s32(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const MergeArgs a,
+                                                                           const __grid_constant__ CUtensorMap tmap) {
+    constexpr int G = 4;
+    constexpr uint32_t STAGE = G * REC;
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint8_t *ring = smem + (size_t)warp * (S * G * REC);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * S * G * REC) + warp * S;
+    const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (S * STAGE);
+    const uint32_t bars = smem_u32(smem) + (uint32_t)WARPS * (S * STAGE) + (uint32_t)warp * (S * 8);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < S; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < S; ++i) mbar_init32(bars + 8 * i, 1);
         mbar_fence_init();
     }
     __syncwarp();
@@ -197,64 +284,93 @@ __global__ void __launch_bounds__(WARPS * 32) merge_tma_kernel(const MergeArgs a
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t n_warps = (int64_t)gridDim.x * WARPS;
     const uint8_t *__restrict__ in = a.in;
-    uint32_t gcount = 0;  // groups consumed so far by this warp (ring position / phase bookkeeping)
+    const uint32_t in_stride = (uint32_t)a.in_stride;
+    // ring positions persist across ranges (every range drains its pipeline, so both end up equal)
+    uint32_t slot_p = 0, slot_c = 0, par_c = 0;
 
     for (int64_t w = gwarp; w < a.n_ranges; w += n_warps) {
         const int64_t s = w * a.quantum;
-        const int64_t e = min(s + (int64_t)a.quantum, a.nnz);
-        if (s >= e) continue;
-        const int n_groups = (int)((e - s + G - 1) / G);
-        RowState st;
+        const int n_pos = (int)min((int64_t)a.quantum, a.nnz - s);
+        if (n_pos <= 0) continue;
+        const int n_groups = (n_pos + G - 1) / G;
+        // s is a multiple of 32 and colidx is 16-byte aligned: the ids of a full group are one aligned int4
+        const int32_t *__restrict__ ids_ptr = a.colidx + s;
+        auto load_ids = [&](int g) {
+            if (g * G + G <= n_pos) return __ldg(reinterpret_cast<const int4 *>(ids_ptr) + g);
+            int4 r;  // ragged tail of the last range: never read past nnz; missing ids repeat the first
+            r.x = __ldg(ids_ptr + g * G);
+            r.y = (g * G + 1 < n_pos) ? __ldg(ids_ptr + g * G + 1) : r.x;
+            r.z = (g * G + 2 < n_pos) ? __ldg(ids_ptr + g * G + 2) : r.x;
+            r.w = r.x;
+            return r;
+        };
 
-        // producer state: ids of the 32-position block the next group to issue falls into
         int issued = 0;
-        int32_t p_ids = (s + lane < e) ? __ldg(a.colidx + s + lane) : 0;
-        int32_t p_next = (s + 32 + lane < e) ? __ldg(a.colidx + s + 32 + lane) : 0;
+        int4 ids_next = make_int4(0, 0, 0, 0);
+        if (lane == 0) ids_next = load_ids(0);
 
         auto issue = [&]() {
-            const int g = issued;
-            const int off = g * G;  // position offset inside the range
-            if (g > 0 && (off & 31) == 0) {
-                p_ids = p_next;
-                p_next = (s + off + 32 + lane < e) ? __ldg(a.colidx + s + off + 32 + lane) : 0;
+            if (lane == 0) {
+                const int4 ids = ids_next;
+                if (issued + 1 < n_groups) ids_next = load_ids(issued + 1);
+                const uint32_t bar = bars + 8 * slot_p;
+                const uint32_t dst = ring + slot_p * STAGE;
+                mbar_expect32(bar, STAGE);  // always 4 rows: a ragged group re-reads its first row
+                if (GATHER4) {
+                    tma_gather4(dst, &tmap, bar, 0, ids.x, ids.y, ids.z, ids.w);
+                } else {
+                    bulk_g2s32(dst, in + (uint64_t)(uint32_t)ids.x * in_stride, REC, bar);
+                    bulk_g2s32(dst + REC, in + (uint64_t)(uint32_t)ids.y * in_stride, REC, bar);
+                    bulk_g2s32(dst + 2 * REC, in + (uint64_t)(uint32_t)ids.z * in_stride, REC, bar);
+                    bulk_g2s32(dst + 3 * REC, in + (uint64_t)(uint32_t)ids.w * in_stride, REC, bar);
+                }
             }
-            const int cnt = (int)min((int64_t)G, e - s - off);
-            const uint32_t slot = (gcount + (uint32_t)g) % S;
-            const int c = __shfl_sync(FULL, p_ids, (off + (lane & (G - 1))) & 31);
-            if (lane == 0) mbar_arrive_expect_tx(bars + slot, (uint32_t)cnt * REC);
-            __syncwarp();
-            if (lane < cnt) bulk_g2s(ring + ((size_t)slot * G + lane) * REC, in + (int64_t)c * a.in_stride, REC, bars + slot);
-            issued = g + 1;
+            issued += 1;
+            slot_p = (slot_p + 1 == S) ? 0 : slot_p + 1;
         };
 
         const int prologue = n_groups < S ? n_groups : S;
         for (int i = 0; i < prologue; ++i) issue();
+        RowState st;
         begin_range(a, st, s);
 
+        int pos = 0;
         for (int g = 0; g < n_groups; ++g) {
-            const uint32_t gi = gcount + (uint32_t)g;
-            const uint32_t slot = gi % S;
-            mbar_wait(bars + slot, (gi / S) & 1u);
-            const int cnt = (int)min((int64_t)G, e - s - (int64_t)g * G);
-            const uint8_t *rows = ring + (size_t)slot * G * REC;
-#pragma unroll
-            for (int l = 0; l < G; ++l) {
-                if (l < cnt) {
-                    const int64_t pos = s + (int64_t)g * G + l;
-                    const uint4 m = *reinterpret_cast<const uint4 *>(rows + l * REC + lane * 16);
-                    const uint2 h = *reinterpret_cast<const uint2 *>(rows + l * REC + REC_MH + lane * 8);
-                    while (pos == st.re) {
-                        flush_row(a, st, w, s, e, lane);
-                        advance_row(a, st);
-                    }
-                    acc_merge(st, m, h);
+            mbar_wait32(bars + 8 * slot_c, par_c);
+            const int cnt = min(G, n_pos - g * G);
+            const uint32_t rows = ring + slot_c * STAGE + lane * 16;
+            const uint32_t rows_h = ring + slot_c * STAGE + REC_MH + lane * 8;
+            int l = 0;
+            while (l < cnt) {
+                while (pos == st.re) {
+                    flush_row(a, st, w, n_pos, lane);
+                    advance_row(a, st, s);
                 }
+                if (l + 1 < cnt && pos + 1 < st.re) {
+                    const uint4 m1 = lds_u4(rows + l * REC);
+                    const uint2 h1 = lds_u2(rows_h + l * REC);
+                    const uint4 m2 = lds_u4(rows + (l + 1) * REC);
+                    const uint2 h2 = lds_u2(rows_h + (l + 1) * REC);
+                    acc_merge2(st, m1, h1, m2, h2);
+                    l += 2;
+                    pos += 2;
+                } else {
+                    const uint4 m1 = lds_u4(rows + l * REC);
+                    const uint2 h1 = lds_u2(rows_h + l * REC);
+                    acc_merge(st, m1, h1);
+                    l += 1;
+                    pos += 1;
+                }
+            }
+            slot_c += 1;
+            if (slot_c == S) {
+                slot_c = 0;
+                par_c ^= 1u;
             }
             __syncwarp();  // every lane has finished reading the slot before it is refilled
             if (issued < n_groups) issue();
         }
-        flush_row(a, st, w, s, e, lane);
-        gcount += (uint32_t)n_groups;
+        flush_row(a, st, w, n_pos, lane);
     }
 }
 
@@ -278,7 +394,9 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
         acc_reset(st);
         {
             const uint8_t *p = a.scratch + (2 * w + 1) * (int64_t)REC;
-            acc_merge(st, ld_nc_u4(p + lane * 16), ld_nc_u2(p + REC_MH + lane * 8));
+            const uint4 m0 = ld_nc_u4(p + lane * 16);
+            const uint2 h0 = ld_nc_u2(p + REC_MH + lane * 8);
+            acc_merge(st, m0, h0);
         }
         for (int64_t x = w + 1; x <= w_end; x += 4) {
             uint4 m[4];
@@ -296,10 +414,11 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
                 if (x + u <= w_end) acc_merge(st, m[u], h[u]);
         }
         uint8_t *dst = a.out + last * a.out_stride;
+        const uint2 hl = acc_hll(st);
         st_na_u4(dst + lane * 16, st.mh);
-        st_na_u2(dst + REC_MH + lane * 8, st.hl);
+        st_na_u2(dst + REC_MH + lane * 8, hl);
         if (a.cards) {
-            float c = ROW_CARD(a, st.hl);
+            float c = ROW_CARD(a, hl);
             if (lane == 0) a.cards[last * a.cards_stride] = c;
         }
     }
@@ -453,8 +572,82 @@ static int resident_grid(K kernel, int block, size_t smem, int *out_grid) {
     return SS_OK;
 }
 
-constexpr int TMA_G = 4, TMA_S = 4, TMA_WARPS = 8;
-constexpr size_t TMA_SMEM = (size_t)TMA_WARPS * TMA_S * TMA_G * REC + TMA_WARPS * TMA_S * 8;
+// ---- tensor map of the previous-hop table for the gather4 engine ---------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved at run time so the library links against
+// the CUDA runtime only (and still builds on a machine without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D map over [n_rows x 192 uint32] with row pitch `stride` bytes; box = one row (gather4 fetches 4 boxes)
+static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_rows, int64_t stride) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SS_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)(REC / 4), (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)stride};
+    cuuint32_t box[2] = {(cuuint32_t)(REC / 4), 1};
+    cuuint32_t elem[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, elem,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld stride=%lld)", (int)r, (long long)n_rows,
+                  (long long)stride);
+        return SS_ERR_CUDA;
+    }
+    return SS_OK;
+}
+
+// TMA engine configurations: (stages, warps per CTA, CTAs per SM).  Shared memory per warp = stages * 3 KB.
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4>
+static int launch_tma(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
+    constexpr size_t smem = (size_t)WARPS * S * 4 * REC + WARPS * S * 8;
+    auto k = merge_tma_kernel<S, WARPS, MIN_CTAS, GATHER4>;
+    SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = 0, rc;
+    if ((rc = resident_grid(k, WARPS * 32, smem, &grid)) != SS_OK) return rc;
+    int64_t blocks = (a.n_ranges + WARPS - 1) / WARPS;
+    if (blocks < grid) grid = (int)blocks;
+    k<<<grid, WARPS * 32, smem, st>>>(a, tmap);
+    SS_LAUNCH_CHECK("merge_tma_kernel");
+    return SS_OK;
+}
+
+// measured on B200 (tools/tune_merge.py, profiles/r01_merge_tuning.txt): 24 warps x 3 stages wins while the
+// tables are a few GB; on the largest graphs 16 warps x 4 stages (deeper per-warp pipeline) is ahead
+static int tma_config(int64_t nnz) {
+    const char *e = getenv("SS_B200_TMA_CFG");  // tuning knob
+    if (e) return atoi(e);
+    return nnz >= (1ll << 28) ? 0 : 1;
+}
+
+template <bool GATHER4>
+static int launch_tma_cfg(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
+    switch (tma_config(a.nnz)) {
+        case 0: return launch_tma<4, 4, 4, GATHER4>(a, tmap, st);   // 16 warps / SM, 4 stages
+        case 2: return launch_tma<2, 4, 8, GATHER4>(a, tmap, st);   // 32 warps / SM, 2 stages
+        case 3: return launch_tma<6, 4, 3, GATHER4>(a, tmap, st);   // 12 warps / SM, 6 stages
+        case 4: return launch_tma<3, 8, 3, GATHER4>(a, tmap, st);   // 24 warps / SM, 3 stages, 8-warp CTAs
+        default: return launch_tma<3, 4, 6, GATHER4>(a, tmap, st);  // 24 warps / SM, 3 stages
+    }
+}
 
 }  // namespace ss
 
@@ -471,17 +664,19 @@ int64_t ss_merge_workspace_bytes(int64_t nnz, int num_perm, int hll_p) {
 }
 
 int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
-                  int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p, void *workspace,
+                  int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p, void *workspace,
                   int64_t workspace_bytes, float *cards_out, int64_t cards_stride, const ss_hll_consts *hc, int variant,
                   ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
-    SS_REQUIRE(n_rows >= 0 && nnz >= 0, "negative size passed to ss_khop_merge");
+    SS_REQUIRE(n_rows >= 0 && nnz >= 0 && in_rows >= 0, "negative size passed to ss_khop_merge");
+    SS_REQUIRE(in_rows < (1ll << 31), "at most 2^31-1 rows in the previous-hop table");
     if (n_rows == 0) return SS_OK;
     SS_REQUIRE(n_rows < (1ll << 31), "at most 2^31-1 rows per call");
     SS_REQUIRE(rowptr && rec_in && rec_out, "null pointer passed to ss_khop_merge");
     SS_REQUIRE(nnz == 0 || colidx, "colidx is null");
     SS_REQUIRE((((uintptr_t)rec_in | (uintptr_t)rec_out) & 15) == 0, "record tables must be 16-byte aligned");
+    SS_REQUIRE(((uintptr_t)colidx & 15) == 0, "colidx must be 16-byte aligned");
     SS_REQUIRE(in_stride >= s.bytes && out_stride >= s.bytes && ((in_stride | out_stride) & 15) == 0,
                "record strides must be >= %d and multiples of 16", s.bytes);
     ss::HllDev hd;
@@ -525,14 +720,17 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
     }
     int grid = 0, rc;
     if (nnz > 0) {
-        if (variant == SS_MERGE_TMA) {
-            auto k = ss::merge_tma_kernel<ss::TMA_G, ss::TMA_S, ss::TMA_WARPS>;
-            SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss::TMA_SMEM));
-            if ((rc = ss::resident_grid(k, ss::TMA_WARPS * 32, ss::TMA_SMEM, &grid)) != SS_OK) return rc;
-            int64_t blocks = (a.n_ranges + ss::TMA_WARPS - 1) / ss::TMA_WARPS;
-            if (blocks < grid) grid = (int)blocks;
-            k<<<grid, ss::TMA_WARPS * 32, ss::TMA_SMEM, st>>>(a);
-            SS_LAUNCH_CHECK("merge_tma_kernel");
+        if (variant == SS_MERGE_TMA || variant == SS_MERGE_BULK) {
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            if (variant == SS_MERGE_TMA) {
+                // rows addressed by colidx are < 2^31; the map covers every row the caller's table can hold
+                if ((rc = ss::make_row_gather_map(&tmap, rec_in, in_rows, in_stride)) != SS_OK) return rc;
+                rc = ss::launch_tma_cfg<true>(a, tmap, st);
+            } else {
+                rc = ss::launch_tma_cfg<false>(a, tmap, st);
+            }
+            if (rc != SS_OK) return rc;
         } else if (variant == SS_MERGE_LDG) {
             auto k = ss::merge_ldg_kernel<8>;
             if ((rc = ss::resident_grid(k, 256, 0, &grid)) != SS_OK) return rc;

@@ -425,7 +425,7 @@ class ElphHashes(object):
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
         ev = self._event_begin(device)
-        check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.stride(0),
+        check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0], rec_in.stride(0),
                                 _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p, _ptr(ws), ws.numel(),
                                 _ptr(cards_col), cards_col.stride(0) if cards_col is not None else 0,
                                 ctypes.byref(d['hc']), _lib.MERGE_VARIANTS[self.merge_variant],

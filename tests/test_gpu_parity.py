@@ -21,7 +21,7 @@ def engine_for(blob, use_zero_one=False, floor_sf=False, variant='auto'):
 
 
 def variants_for(blob):
-    return ['auto', 'tma', 'ldg', 'generic'] if (int(blob['P']), int(blob['p'])) == (128, 8) else ['auto']
+    return ['auto', 'tma', 'bulk', 'ldg', 'generic'] if (int(blob['P']), int(blob['p'])) == (128, 8) else ['auto']
 
 
 @pytest.mark.parametrize('name', GRAPH_CASES)
@@ -112,7 +112,7 @@ def test_rmat_with_hubs_vs_oracle(K, seed):
     of = o.subgraph_features(links, ot, oc)
     deg = torch.bincount(ei[1], minlength=n)
     assert int(deg.max()) > 512  # a real hub
-    for variant in ('tma', 'ldg', 'generic'):
+    for variant in ('tma', 'bulk', 'ldg', 'generic'):
         eh = ssb.ElphHashes(make_args(K), merge_variant=variant)
         tables, cards = eh.build_hash_tables(n, ei.to(DEV))
         for k in range(K + 1):
