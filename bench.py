@@ -218,7 +218,7 @@ def main():
 
     import subgraph_sketching_b200 as ssb
     from subgraph_sketching_b200 import _lib
-    from subgraph_sketching_b200.dist import ShardedElphHashes, link_slice, shard_bounds
+    from subgraph_sketching_b200.dist import ShardedElphHashes, link_slice
 
     N, K, L = spec['num_nodes'], spec['hops'], spec['links']
     F = K * (K + 2)
@@ -281,10 +281,8 @@ def main():
     # ---- roofline of the dominant kernel (k-hop merge) -----------------------------------------------
     R = 768
     if distributed:
-        _, lo, hi = shard_bounds(N, world, rank)
-        rows_local = hi - lo
-        nnz_local = int(((ei[1] >= lo) & (ei[1] < hi)).sum()) if n_edges else 0
-        nnz_local += max(0, min(hi, int(ei.max()) + 1) - lo)
+        rows_local = eng.bounds[rank + 1] - eng.bounds[rank]
+        nnz_local = eng.local_nnz
     else:
         rows_local, nnz_local = N, nnz
     merge_bytes = nnz_local * R + rows_local * R + 4 * nnz_local + 8 * (rows_local + 1) + 4 * rows_local
@@ -361,7 +359,7 @@ def main():
             'dtype': 'u32/u8 sketches, f32 estimates', 'data': 'synthetic',
             'config': {'workload': spec['name'], 'num_nodes': N, 'directed_edges': n_edges, 'nnz_with_self_loops': nnz,
                        'hops': K, 'num_perm': 128, 'hll_p': 8, 'links_per_step': L, 'features_per_link': F,
-                       'merge_variant': a.merge_variant, 'partition': f'node-sharded x{world}' if distributed else 'single',
+                       'merge_variant': a.merge_variant, 'partition': f'node-sharded x{world} (row blocks balanced by neighbour count)' if distributed else 'single',
                        'l2': 'inputs larger than L2 (each hop table is N*768 B), no explicit flush'},
             'features_per_s': value * F,
             'stage_ms_per_step': {k: sum(v) / a.steps for k, v in stage_ms.items()},

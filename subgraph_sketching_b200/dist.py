@@ -2,10 +2,15 @@
 
 The path shards naturally by destination node: rank r owns a contiguous block of rows of every
 hop table and the CSR rows of those destinations.  One hop = local k-hop merge of the owned rows (reads the
-full previous-hop table, writes the owned slice of the next one) followed by ONE all-gather of the owned
-slices (NCCL over NVLink / NVSwitch), after which every rank holds the full hop table again.  After the last
-hop the tables are replicated, so candidate links shard trivially: each rank computes the features of its
-slice of the link list with no further communication.
+full previous-hop table, writes the owned block of the next one) followed by ONE exchange step in which every
+rank's block is replicated to all others (NCCL over NVLink / NVSwitch), after which every rank holds the full
+hop table again.  After the last hop the tables are replicated, so candidate links shard trivially: each
+rank computes the features of its slice of the link list with no further communication.
+
+Row blocks are balanced by NEIGHBOUR COUNT, not by row count: on power-law graphs the low ids are the hubs
+(equal row blocks gave rank 0 74 % of the edges of an R-MAT-24 graph at 2 ranks), so the block boundaries are
+the quantiles of the global rowptr.  Blocks therefore differ in size and the exchange is one broadcast per
+owner block (same bytes on the wire as an all-gather).
 
 The reference has no distributed code at all (src/hashing.py is single process); results are bit-identical
 to the single-GPU engine because min/max merges do not depend on the partition.
@@ -15,11 +20,12 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from .hashing import ElphHashes, HopSketch, SketchTables, build_csr, _to_host
+from . import _lib
+from .hashing import ElphHashes, HopSketch, SketchTables, _ptr, _stream_ptr, _to_device, check, lib
 
 
 def shard_bounds(num_nodes, world_size, rank):
-    """contiguous row block of `rank`: equal blocks of ceil(N / G) rows, the last ones may be short/empty"""
+    """equal contiguous blocks of ceil(N / G) rows (the last ones may be short / empty)"""
     per = (num_nodes + world_size - 1) // world_size if world_size > 0 else num_nodes
     lo = min(rank * per, num_nodes)
     hi = min(lo + per, num_nodes)
@@ -32,15 +38,32 @@ def link_slice(n_links, world_size, rank):
     return lo, min(lo + per, n_links)
 
 
-def allgather_rows(full, per, rank, world_size, group=None):
-    """in-place all-gather: rank r's rows [r*per, (r+1)*per) of `full` ([G*per, ...]) are sent to everyone"""
-    assert full.shape[0] == per * world_size
-    mine = full[rank * per:(rank + 1) * per]
-    if dist.get_backend(group) == 'nccl':
-        dist.all_gather_into_tensor(full, mine, group=group)
-    else:  # gloo (CPU tests): list form, out-of-place input
-        parts = [full[r * per:(r + 1) * per] for r in range(world_size)]
-        dist.all_gather(parts, mine.clone(), group=group)
+def balanced_bounds(rowptr, world_size):
+    """row boundaries [b_0 = 0, ..., b_G = N] such that every block holds ~ nnz / G neighbours.
+    `rowptr` is the global int64 [N + 1] prefix sum (any device); returns a python list of G + 1 ints."""
+    n = rowptr.numel() - 1
+    if n <= 0:
+        return [0] * (world_size + 1)
+    nnz = int(rowptr[-1])
+    targets = torch.tensor([(nnz * r) // world_size for r in range(1, world_size)], dtype=rowptr.dtype,
+                           device=rowptr.device)
+    cuts = torch.searchsorted(rowptr, targets, right=False).clamp_(0, n).tolist() if world_size > 1 else []
+    bounds = [0] + [int(c) for c in cuts] + [n]
+    for i in range(1, len(bounds)):  # monotone, in range
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def exchange_blocks(full, bounds, group=None):
+    """replicate every owner block full[bounds[r]:bounds[r+1]] from rank r to all ranks (in place)"""
+    works = []
+    for r in range(len(bounds) - 1):
+        lo, hi = bounds[r], bounds[r + 1]
+        if hi > lo:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            works.append(dist.broadcast(full[lo:hi], src=src, group=group, async_op=True))
+    for w in works:
+        w.wait()
     return full
 
 
@@ -54,37 +77,63 @@ class ShardedElphHashes(object):
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.bounds = None
+        self.local_nnz = None
+
+    def _local_csr(self, edge_index, num_nodes, device):
+        """global rowptr (every rank computes the same one) -> balanced bounds -> this rank's CSR rows"""
+        ei = _to_device(edge_index, device)
+        ei = (ei if ei.dtype == torch.int64 else ei.long()).contiguous()
+        n_edges = ei.shape[1]
+        max_id = int(ei.max()) if n_edges else -1
+        if max_id >= num_nodes:
+            raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
+        n_loops = max_id + 1
+        src, dst = ei[0], ei[1]
+        ws_bytes = check(lib.ss_csr_workspace_bytes(num_nodes), 'ss_csr_workspace_bytes')
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
+        rowptr_g = torch.empty(num_nodes + 1, dtype=torch.int64, device=device)
+        st = _stream_ptr(device)
+        check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, n_loops, 0, num_nodes, _ptr(rowptr_g), _ptr(ws),
+                                ws.numel(), st), 'ss_csr_rowptr')
+        bounds = balanced_bounds(rowptr_g, self.world_size)
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        rowptr = (rowptr_g[lo:hi + 1] - rowptr_g[lo]).contiguous()
+        nnz = int(rowptr[-1]) if hi > lo else 0
+        colidx = torch.empty(max(nnz, 4), dtype=torch.int32, device=device)
+        if hi > lo:
+            check(lib.ss_csr_fill(_ptr(src), _ptr(dst), n_edges, n_loops, lo, hi - lo, _ptr(rowptr), _ptr(colidx),
+                                  _ptr(ws), ws.numel(), st), 'ss_csr_fill')
+        return rowptr, colidx, nnz, bounds
 
     def build_hash_tables(self, num_nodes, edge_index):
-        eh, G, r = self.eh, self.world_size, self.rank
-        device = edge_index.device
-        assert device.type == 'cuda', 'the sharded build takes device-resident edges'
-        per, lo, hi = shard_bounds(num_nodes, G, r)
+        eh, r = self.eh, self.rank
+        _lib.require_cuda()
+        device = edge_index.device if edge_index.is_cuda else torch.device('cuda', torch.cuda.current_device())
         K = eh.max_hops
         with torch.cuda.device(device):
             ev = eh._event_begin(device)
-            rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=hi - lo, add_loops=True, row_begin=lo)
+            rowptr, colidx, nnz, bounds = self._local_csr(edge_index, num_nodes, device)
             eh._event_end('csr_build', ev, device)
-            if max_id >= num_nodes:
-                raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
+            self.bounds, self.local_nnz = bounds, nnz
+            lo, hi = bounds[r], bounds[r + 1]
             rb = eh._record_bytes()
-            n_pad = per * G
-            recs = [torch.empty((n_pad, rb), dtype=torch.uint8, device=device) for _ in range(K + 1)]
-            cards = torch.zeros((n_pad, K), dtype=torch.float32, device=device)
+            recs = [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(K + 1)]
+            cards = torch.zeros((num_nodes, K), dtype=torch.float32, device=device)
             ev = eh._event_begin(device)
-            eh._init_records(num_nodes, device, out=recs[0][:num_nodes])  # hop 0 is cheap: no exchange needed
+            eh._init_records(num_nodes, device, out=recs[0])  # hop 0 is cheap: computed redundantly, no exchange
             eh._event_end('init_records', ev, device)
             ws = None
             for k in range(1, K + 1):
                 if hi > lo:
                     ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device, ws)
                 ev = eh._event_begin(device)
-                allgather_rows(recs[k], per, r, G, self.group)
-                eh._event_end('allgather', ev, device)
-            allgather_rows(cards, per, r, G, self.group)
-            tables = SketchTables({k: HopSketch(recs[k][:num_nodes], eh.num_perm, eh.p, device) for k in range(K + 1)},
+                exchange_blocks(recs[k], bounds, self.group)
+                eh._event_end('exchange', ev, device)
+            exchange_blocks(cards, bounds, self.group)
+            tables = SketchTables({k: HopSketch(recs[k], eh.num_perm, eh.p, device) for k in range(K + 1)},
                                   eh.num_perm, eh.p)
-            return tables, cards[:num_nodes]
+            return tables, cards
 
     def get_subgraph_features(self, links, hash_table, cards, batch_size=11000000):
         """features of this rank's slice of `links` (rows link_slice(len(links), G, rank))"""

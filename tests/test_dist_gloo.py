@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from subgraph_sketching_b200.dist import allgather_rows, link_slice, shard_bounds
+from subgraph_sketching_b200.dist import balanced_bounds, exchange_blocks, link_slice, shard_bounds
 
 
 def test_shard_bounds_cover_all_rows():
@@ -30,30 +30,45 @@ def _free_port():
     return port
 
 
+def test_balanced_bounds_split_neighbours_evenly():
+    g = torch.Generator().manual_seed(0)
+    # power-law in-degrees: the low ids are hubs, like R-MAT
+    deg = (1000.0 / (1.0 + torch.arange(5000.0)) + 1).long() + torch.randint(0, 3, (5000,), generator=g)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(deg, 0)])
+    nnz = int(rowptr[-1])
+    for G in (1, 2, 4, 8):
+        b = balanced_bounds(rowptr, G)
+        assert b[0] == 0 and b[-1] == 5000 and len(b) == G + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        shares = [int(rowptr[b[r + 1]] - rowptr[b[r]]) for r in range(G)]
+        assert sum(shares) == nnz
+        assert max(shares) <= nnz / G + int(deg.max()), (G, shares)
+    assert balanced_bounds(torch.zeros(1, dtype=torch.long), 4) == [0, 0, 0, 0, 0]
+    assert balanced_bounds(torch.zeros(6, dtype=torch.long), 2)[-1] == 5
+
+
 def _worker(rank, world, port, n, width):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        per, lo, hi = shard_bounds(n, world, rank)
-        full = torch.full((per * world, width), 255, dtype=torch.uint8)
-        # each rank fills its own block with a rank/row specific pattern
+        bounds = [0, 9, n]  # deliberately unequal blocks
+        lo, hi = bounds[rank], bounds[rank + 1]
+        full = torch.full((n, width), 255, dtype=torch.uint8)
         rows = torch.arange(lo, hi).view(-1, 1)
         full[lo:hi] = ((rows * 7 + torch.arange(width).view(1, -1) + rank) % 251).to(torch.uint8)
-        allgather_rows(full, per, rank, world)
+        exchange_blocks(full, bounds)
         for r in range(world):
-            _, a, b = shard_bounds(n, world, r)
+            a, b = bounds[r], bounds[r + 1]
             rr = torch.arange(a, b).view(-1, 1)
             want = ((rr * 7 + torch.arange(width).view(1, -1) + r) % 251).to(torch.uint8)
             assert torch.equal(full[a:b], want), f'rank {rank}: block of rank {r} wrong'
-        cards = torch.zeros((per * world, 3))
+        cards = torch.zeros((n, 3))
         cards[lo:hi] = rank + 1.0
-        allgather_rows(cards, per, rank, world)
-        assert float(cards[:n].sum()) == sum((shard_bounds(n, world, r)[2] - shard_bounds(n, world, r)[1]) * (r + 1.0) * 3
-                                             for r in range(world))
+        exchange_blocks(cards, bounds)
+        assert float(cards.sum()) == sum((bounds[r + 1] - bounds[r]) * (r + 1.0) * 3 for r in range(world))
     finally:
         dist.destroy_process_group()
 
 
-def test_allgather_layout_world2():
+def test_exchange_layout_world2():
     mp.spawn(_worker, args=(2, _free_port(), 37, 48), nprocs=2, join=True)
