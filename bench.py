@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--ref-scale', type=int, default=15, help='R-MAT scale of each --impl reference step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'nccl'], help='multi-GPU exchange mode')
     ap.add_argument('--seed', type=int, default=0)
     return ap.parse_args()
 
@@ -227,7 +228,7 @@ def main():
     n_edges = int(ei.shape[1])
     nnz = n_edges + min(int(ei.max()) + 1, N)
     if distributed:
-        eng = ShardedElphHashes(engine_args(K), merge_variant=a.merge_variant)
+        eng = ShardedElphHashes(engine_args(K), merge_variant=a.merge_variant, exchange=a.exchange)
         eh = eng.eh
     else:
         eng = eh = ssb.ElphHashes(engine_args(K), merge_variant=a.merge_variant)
@@ -359,7 +360,8 @@ def main():
             'dtype': 'u32/u8 sketches, f32 estimates', 'data': 'synthetic',
             'config': {'workload': spec['name'], 'num_nodes': N, 'directed_edges': n_edges, 'nnz_with_self_loops': nnz,
                        'hops': K, 'num_perm': 128, 'hll_p': 8, 'links_per_step': L, 'features_per_link': F,
-                       'merge_variant': a.merge_variant, 'partition': f'node-sharded x{world} (row blocks balanced by neighbour count)' if distributed else 'single',
+                       'merge_variant': a.merge_variant, 'partition': (f'node-sharded x{world} (row blocks balanced by neighbour count), exchange={eng.exchange}'
+                                     if distributed else 'single'),
                        'l2': 'inputs larger than L2 (each hop table is N*768 B), no explicit flush'},
             'features_per_s': value * F,
             'stage_ms_per_step': {k: sum(v) / a.steps for k, v in stage_ms.items()},

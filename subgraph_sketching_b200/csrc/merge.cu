@@ -48,6 +48,11 @@ struct MergeArgs {
     float *cards;
     int64_t cards_stride;
     HllDev h;
+    // fused exchange (multi-GPU): peer copies of `out` / `cards`, mapped into this process (NVLink P2P);
+    // every finished row is also stored there, so the next-hop table is replicated when the launch ends
+    int n_peers;
+    uint8_t *peer_out[SS_MAX_PEERS];
+    float *peer_cards[SS_MAX_PEERS];
 };
 
 // HLL++ estimate of a row held as 8 registers per lane.  Not inlined: it is called once per output row
@@ -69,6 +74,24 @@ __device__ __noinline__ float row_cardinality(uint2 hl, int m, int T, int monoto
 #define ROW_CARD(a, hl) \
     row_cardinality(hl, (a).h.m, (a).h.T, (a).h.monotone, (a).h.threshold, (a).h.alpha_m2, (a).h.five_m, (a).h.lc, \
                     (a).h.est, (a).h.bias)
+
+// final store of output row `row`: local table, its cardinality, and the same to every peer table
+__device__ __forceinline__ void store_row(const MergeArgs &a, int64_t row, const uint4 &mh, const uint2 &hl, int lane) {
+    const int64_t off = row * a.out_stride;
+    st_na_u4(a.out + off + lane * 16, mh);
+    st_na_u2(a.out + off + REC_MH + lane * 8, hl);
+    for (int p = 0; p < a.n_peers; ++p) {
+        st_na_u4(a.peer_out[p] + off + lane * 16, mh);
+        st_na_u2(a.peer_out[p] + off + REC_MH + lane * 8, hl);
+    }
+    if (a.cards) {
+        float c = ROW_CARD(a, hl);
+        if (lane == 0) {
+            a.cards[row * a.cards_stride] = c;
+            for (int p = 0; p < a.n_peers; ++p) a.peer_cards[p][row * a.cards_stride] = c;
+        }
+    }
+}
 
 // first row whose neighbour range contains position `pos` (0 <= pos < nnz): largest r with rowptr[r] <= pos
 __device__ __forceinline__ int64_t row_of_position(const int64_t *__restrict__ rowptr, int64_t n_rows, int64_t pos) {
@@ -131,14 +154,13 @@ __device__ __forceinline__ uint2 acc_hll(const RowState &st) { return make_uint2
 // write the finished (or partial) current row; n_pos = length of the range, w = range index
 __device__ __forceinline__ void flush_row(const MergeArgs &a, const RowState &st, int64_t w, int n_pos, int lane) {
     if (st.rs == st.re) return;  // empty rows are zero-filled by the fix-up kernel
-    const bool whole = st.rs >= 0 && st.re <= n_pos;
-    uint8_t *dst = whole ? a.out + (int64_t)st.cur * a.out_stride : a.scratch + (2 * w + (st.rs < 0 ? 0 : 1)) * (int64_t)REC;
     const uint2 hl = acc_hll(st);
-    st_na_u4(dst + lane * 16, st.mh);
-    st_na_u2(dst + REC_MH + lane * 8, hl);
-    if (whole && a.cards) {
-        float c = ROW_CARD(a, hl);
-        if (lane == 0) a.cards[(int64_t)st.cur * a.cards_stride] = c;
+    if (st.rs >= 0 && st.re <= n_pos) {
+        store_row(a, st.cur, st.mh, hl, lane);
+    } else {  // cut by a range boundary: partial record for the fix-up kernel
+        uint8_t *dst = a.scratch + (2 * w + (st.rs < 0 ? 0 : 1)) * (int64_t)REC;
+        st_na_u4(dst + lane * 16, st.mh);
+        st_na_u2(dst + REC_MH + lane * 8, hl);
     }
 }
 
@@ -413,14 +435,7 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
             for (int u = 0; u < 4; ++u)
                 if (x + u <= w_end) acc_merge(st, m[u], h[u]);
         }
-        uint8_t *dst = a.out + last * a.out_stride;
-        const uint2 hl = acc_hll(st);
-        st_na_u4(dst + lane * 16, st.mh);
-        st_na_u2(dst + REC_MH + lane * 8, hl);
-        if (a.cards) {
-            float c = ROW_CARD(a, hl);
-            if (lane == 0) a.cards[last * a.cards_stride] = c;
-        }
+        store_row(a, last, st.mh, acc_hll(st), lane);
     }
     // (B) rows without any in-edge: all-zero record (scatter-max fill value), cardinality of an empty sketch
     for (int64_t r0 = gwarp * 32; r0 < a.n_rows; r0 += n_warps * 32) {
@@ -430,13 +445,7 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            uint8_t *dst = a.out + (r0 + b) * a.out_stride;
-            st_na_u4(dst + lane * 16, make_uint4(0u, 0u, 0u, 0u));
-            st_na_u2(dst + REC_MH + lane * 8, make_uint2(0u, 0u));
-            if (a.cards) {
-                float c = ROW_CARD(a, make_uint2(0u, 0u));
-                if (lane == 0) a.cards[(r0 + b) * a.cards_stride] = c;
-            }
+            store_row(a, r0 + b, make_uint4(0u, 0u, 0u, 0u), make_uint2(0u, 0u), lane);
         }
     }
 }
@@ -667,6 +676,15 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
                   int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p, void *workspace,
                   int64_t workspace_bytes, float *cards_out, int64_t cards_stride, const ss_hll_consts *hc, int variant,
                   ss_stream_t stream) {
+    return ss_khop_merge_peers(rowptr, colidx, n_rows, nnz, rec_in, in_rows, in_stride, rec_out, out_stride, num_perm, hll_p,
+                               workspace, workspace_bytes, cards_out, cards_stride, hc, variant, 0, nullptr, nullptr, stream);
+}
+
+int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
+                        int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p,
+                        void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
+                        const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
+                        float *const *peer_cards_out, ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n_rows >= 0 && nnz >= 0 && in_rows >= 0, "negative size passed to ss_khop_merge");
@@ -691,6 +709,9 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
     if (variant == SS_MERGE_AUTO) variant = fast_shape ? SS_MERGE_TMA : SS_MERGE_GENERIC;
     SS_REQUIRE(variant == SS_MERGE_GENERIC || fast_shape, "TMA/LDG merge kernels need num_perm=128, hll_p=8");
 
+    SS_REQUIRE(n_peers >= 0 && n_peers <= SS_MAX_PEERS, "n_peers must be in [0, %d]", SS_MAX_PEERS);
+    SS_REQUIRE(n_peers == 0 || (variant != SS_MERGE_GENERIC && peer_rec_out && (!cards_out || peer_cards_out)),
+               "peer stores need the P=128/p=8 engines and one pointer per peer");
     if (variant == SS_MERGE_GENERIC) {
         ss::GenericArgs g;
         g.rowptr = rowptr; g.colidx = colidx; g.n_rows = n_rows;
@@ -712,6 +733,12 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
     a.n_ranges = ss::n_ranges_for(nnz, a.quantum);
     a.scratch = (uint8_t *)workspace;
     a.cards = cards_out; a.cards_stride = cards_stride; a.h = hd;
+    a.n_peers = n_peers;
+    for (int p = 0; p < SS_MAX_PEERS; ++p) {
+        a.peer_out[p] = p < n_peers ? (uint8_t *)peer_rec_out[p] : nullptr;
+        a.peer_cards[p] = (p < n_peers && cards_out) ? peer_cards_out[p] : nullptr;
+        SS_REQUIRE(p >= n_peers || (a.peer_out[p] && ((uintptr_t)a.peer_out[p] & 15) == 0), "peer table %d is null or misaligned", p);
+    }
     const int64_t need = 2 * a.n_ranges * (int64_t)ss::REC;
     SS_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "merge workspace must be a 16-byte aligned device buffer");
     if (workspace_bytes < need) {

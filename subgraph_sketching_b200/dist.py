@@ -12,6 +12,14 @@ Row blocks are balanced by NEIGHBOUR COUNT, not by row count: on power-law graph
 the quantiles of the global rowptr.  Blocks therefore differ in size and the exchange is one broadcast per
 owner block (same bytes on the wire as an all-gather).
 
+Exchange modes
+  'p2p'  (default when symmetric memory works): the hop tables live in symmetric memory
+         (torch.distributed._symmetric_memory: every rank's buffer is mapped into every process over NVLink)
+         and the merge kernel itself stores each finished row into all peer tables (ss_khop_merge_peers), so
+         the exchange is fused into the kernel and overlaps the merge row by row; a stream-ordered
+         symmetric-memory barrier separates the hops.  No NCCL call on the data path.
+  'nccl' one torch.distributed broadcast per owner block after the merge kernel (works everywhere).
+
 The reference has no distributed code at all (src/hashing.py is single process); results are bit-identical
 to the single-GPU engine because min/max merges do not depend on the partition.
 """
@@ -72,13 +80,48 @@ class ShardedElphHashes(object):
     passes the same (replicated) edge_index and link list and gets the full tables plus ITS slice of features
     (`link_slice`)."""
 
-    def __init__(self, args, group=None, **kw):
+    def __init__(self, args, group=None, exchange='auto', **kw):
+        assert exchange in ('auto', 'p2p', 'nccl')
         self.eh = ElphHashes(args, **kw)
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.bounds = None
         self.local_nnz = None
+        self.exchange = exchange
+        self._symm = None       # cached symmetric buffers: (key, recs[1..K], cards, handles)
+        self.exchange_error = None
+        if self.world_size == 1 or self.world_size - 1 > 7:
+            self.exchange = 'nccl'
+
+    # ------------------------------------------------------------------ symmetric-memory tables
+    def _symmetric_buffers(self, num_nodes, K, rb, device):
+        """hop tables 1..K and cards in symmetric memory (allocated once per shape, reused by later builds);
+        returns None (on every rank consistently) when symmetric memory is unavailable"""
+        key = (num_nodes, K, rb, str(device))
+        if self._symm is not None and self._symm[0] == key:
+            return self._symm
+        ok = 1
+        recs, hdls, cards, chdl = [], [], None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            for _ in range(K):
+                t = symm_mem.empty(max(num_nodes, 1) * rb, dtype=torch.uint8, device=device)
+                hdls.append(symm_mem.rendezvous(t, group=grp))
+                recs.append(t.view(max(num_nodes, 1), rb)[:num_nodes])
+            c = symm_mem.empty(max(num_nodes, 1) * K, dtype=torch.float32, device=device)
+            chdl = symm_mem.rendezvous(c, group=grp)
+            cards = c.view(max(num_nodes, 1), K)[:num_nodes]
+        except Exception as e:  # noqa: BLE001 -- any failure means: fall back to NCCL, on every rank
+            ok = 0
+            self.exchange_error = f'{type(e).__name__}: {e}'
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return None
+        self._symm = (key, recs, cards, hdls, chdl)
+        return self._symm
 
     def _local_csr(self, edge_index, num_nodes, device):
         """global rowptr (every rank computes the same one) -> balanced bounds -> this rank's CSR rows"""
@@ -118,19 +161,45 @@ class ShardedElphHashes(object):
             self.bounds, self.local_nnz = bounds, nnz
             lo, hi = bounds[r], bounds[r + 1]
             rb = eh._record_bytes()
-            recs = [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(K + 1)]
-            cards = torch.zeros((num_nodes, K), dtype=torch.float32, device=device)
+            symm = None
+            if self.exchange in ('auto', 'p2p'):
+                symm = self._symmetric_buffers(num_nodes, K, rb, device)
+                if symm is None and self.exchange == 'p2p':
+                    raise RuntimeError(f'symmetric memory is unavailable: {self.exchange_error}')
+                if symm is None:
+                    self.exchange = 'nccl'
+                else:
+                    self.exchange = 'p2p'
+            rec0 = torch.empty((num_nodes, rb), dtype=torch.uint8, device=device)
             ev = eh._event_begin(device)
-            eh._init_records(num_nodes, device, out=recs[0])  # hop 0 is cheap: computed redundantly, no exchange
+            eh._init_records(num_nodes, device, out=rec0)  # hop 0 is cheap: computed redundantly, no exchange
             eh._event_end('init_records', ev, device)
             ws = None
-            for k in range(1, K + 1):
-                if hi > lo:
-                    ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device, ws)
-                ev = eh._event_begin(device)
-                exchange_blocks(recs[k], bounds, self.group)
-                eh._event_end('exchange', ev, device)
-            exchange_blocks(cards, bounds, self.group)
+            if symm is not None:
+                _, srecs, cards, hdls, chdl = symm
+                recs = [rec0] + list(srecs)
+                others = [q for q in range(self.world_size) if q != r]
+                hdls[0].barrier()  # no peer still reads these buffers from an earlier build
+                for k in range(1, K + 1):
+                    if hi > lo:
+                        peer_recs = [int(hdls[k - 1].buffer_ptrs[q]) + lo * rb for q in others]
+                        peer_cards = [int(chdl.buffer_ptrs[q]) + (lo * K + (k - 1)) * 4 for q in others]
+                        ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
+                                       ws, peer_recs, peer_cards)
+                    ev = eh._event_begin(device)
+                    hdls[k - 1].barrier()  # every rank's launch (and its peer stores) has completed
+                    eh._event_end('exchange', ev, device)
+            else:
+                recs = [rec0] + [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(K)]
+                cards = torch.zeros((num_nodes, K), dtype=torch.float32, device=device)
+                for k in range(1, K + 1):
+                    if hi > lo:
+                        ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
+                                       ws)
+                    ev = eh._event_begin(device)
+                    exchange_blocks(recs[k], bounds, self.group)
+                    eh._event_end('exchange', ev, device)
+                exchange_blocks(cards, bounds, self.group)
             tables = SketchTables({k: HopSketch(recs[k], eh.num_perm, eh.p, device) for k in range(K + 1)},
                                   eh.num_perm, eh.p)
             return tables, cards

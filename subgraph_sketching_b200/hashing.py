@@ -418,18 +418,32 @@ class ElphHashes(object):
             return HopSketch(rec, self.num_perm, self.p, torch.device('cpu'))['hll']
 
     # ------------------------------------------------------------------ K2
-    def _merge(self, rowptr, colidx, nnz, rec_in, rec_out, cards_col, device, ws=None):
+    def _merge(self, rowptr, colidx, nnz, rec_in, rec_out, cards_col, device, ws=None, peer_recs=None,
+               peer_cards=None):
+        """one hop over the rows of `rec_out`; peer_recs / peer_cards: device addresses (ints) of the peers'
+        copies of rec_out / cards_col for the fused multi-GPU exchange (ss_khop_merge_peers)"""
         d = self._consts(device)
         n_rows = rec_out.shape[0]
         need = check(lib.ss_merge_workspace_bytes(nnz, self.num_perm, self.p), 'ss_merge_workspace_bytes')
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
         ev = self._event_begin(device)
-        check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0], rec_in.stride(0),
-                                _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p, _ptr(ws), ws.numel(),
-                                _ptr(cards_col), cards_col.stride(0) if cards_col is not None else 0,
-                                ctypes.byref(d['hc']), _lib.MERGE_VARIANTS[self.merge_variant],
-                                _stream_ptr(device)), 'ss_khop_merge')
+        n_peers = len(peer_recs) if peer_recs else 0
+        if n_peers:
+            pr = (ctypes.c_void_p * n_peers)(*peer_recs)
+            pc = (ctypes.c_void_p * n_peers)(*(peer_cards or [0] * n_peers))
+            check(lib.ss_khop_merge_peers(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0],
+                                          rec_in.stride(0), _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p,
+                                          _ptr(ws), ws.numel(), _ptr(cards_col),
+                                          cards_col.stride(0) if cards_col is not None else 0, ctypes.byref(d['hc']),
+                                          _lib.MERGE_VARIANTS[self.merge_variant], n_peers, pr, pc,
+                                          _stream_ptr(device)), 'ss_khop_merge_peers')
+        else:
+            check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0],
+                                    rec_in.stride(0), _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p,
+                                    _ptr(ws), ws.numel(), _ptr(cards_col),
+                                    cards_col.stride(0) if cards_col is not None else 0, ctypes.byref(d['hc']),
+                                    _lib.MERGE_VARIANTS[self.merge_variant], _stream_ptr(device)), 'ss_khop_merge')
         self._event_end('khop_merge', ev, device)
         return ws
 

@@ -21,7 +21,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, scale, K):
+def _worker(rank, world, port, scale, K, exchange='auto'):
     import subgraph_sketching_b200 as ssb
     from subgraph_sketching_b200.dist import ShardedElphHashes, link_slice
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -34,9 +34,14 @@ def _worker(rank, world, port, scale, K):
         ei = rmat_edges(scale, 16, 3).to(dev)
         g = torch.Generator().manual_seed(4)
         links = torch.randint(0, n, (20001, 2), generator=g).to(dev)
-        sh = ShardedElphHashes(make_args(K))
+        sh = ShardedElphHashes(make_args(K), exchange=exchange)
         tables, cards = sh.build_hash_tables(n, ei)
         feats = sh.get_subgraph_features(links, tables, cards)
+        print(f'rank {rank}/{world}: exchange={sh.exchange} ({sh.exchange_error})', flush=True)
+        if exchange != 'auto':
+            assert sh.exchange == exchange
+        # a second build reuses the symmetric buffers and must give the same tables
+        tables, cards = sh.build_hash_tables(n, ei)
         one = ssb.ElphHashes(make_args(K))
         t1, c1 = one.build_hash_tables(n, ei)
         f1 = one.get_subgraph_features(links, t1, c1)
@@ -58,5 +63,6 @@ def test_sharded_world1_matches_single_gpu():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_sharded_world2_matches_single_gpu():
-    mp.spawn(_worker, args=(2, _free_port(), 13, 3), nprocs=2, join=True)
+@pytest.mark.parametrize('exchange', ['nccl', 'auto'])
+def test_sharded_world2_matches_single_gpu(exchange):
+    mp.spawn(_worker, args=(2, _free_port(), 13, 3, exchange), nprocs=2, join=True)
