@@ -46,20 +46,34 @@ def link_slice(n_links, world_size, rank):
     return lo, min(lo + per, n_links)
 
 
-def balanced_bounds(rowptr, world_size):
-    """row boundaries [b_0 = 0, ..., b_G = N] such that every block holds ~ nnz / G neighbours.
-    `rowptr` is the global int64 [N + 1] prefix sum (any device); returns a python list of G + 1 ints."""
+def balanced_bounds(rowptr, world_size, row_weight=0.0):
+    """row boundaries [b_0 = 0, ..., b_G = N] such that every block carries the same COST
+    cost(block) = neighbours(block) + row_weight * rows(block).
+    One neighbour = one 768-byte gather from HBM; a finished row costs one local store plus, in the fused p2p
+    exchange, one 768-byte store per peer over NVLink (about 10x the time of an HBM gather), so the row term
+    dominates at 8 GPUs and vanishes at 1.  `rowptr` is the global int64 [N + 1] prefix sum (any device);
+    returns a python list of G + 1 ints."""
     n = rowptr.numel() - 1
     if n <= 0:
         return [0] * (world_size + 1)
-    nnz = int(rowptr[-1])
-    targets = torch.tensor([(nnz * r) // world_size for r in range(1, world_size)], dtype=rowptr.dtype,
+    if world_size == 1:
+        return [0, n]
+    cost = rowptr.double() + float(row_weight) * torch.arange(n + 1, device=rowptr.device, dtype=torch.float64)
+    total = float(cost[-1])
+    targets = torch.tensor([total * r / world_size for r in range(1, world_size)], dtype=torch.float64,
                            device=rowptr.device)
-    cuts = torch.searchsorted(rowptr, targets, right=False).clamp_(0, n).tolist() if world_size > 1 else []
+    cuts = torch.searchsorted(cost, targets, right=False).clamp_(0, n).tolist()
     bounds = [0] + [int(c) for c in cuts] + [n]
     for i in range(1, len(bounds)):  # monotone, in range
         bounds[i] = max(bounds[i], bounds[i - 1])
     return bounds
+
+
+def default_row_weight(world_size, exchange):
+    """cost of one output row in units of one neighbour gather (measured on B200 / NVLink 5)"""
+    if world_size <= 1:
+        return 0.0
+    return 1.5 + (10.0 * (world_size - 1) if exchange != 'nccl' else 4.0)
 
 
 def exchange_blocks(full, bounds, group=None):
@@ -139,7 +153,7 @@ class ShardedElphHashes(object):
         st = _stream_ptr(device)
         check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, n_loops, 0, num_nodes, _ptr(rowptr_g), _ptr(ws),
                                 ws.numel(), st), 'ss_csr_rowptr')
-        bounds = balanced_bounds(rowptr_g, self.world_size)
+        bounds = balanced_bounds(rowptr_g, self.world_size, default_row_weight(self.world_size, self.exchange))
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         rowptr = (rowptr_g[lo:hi + 1] - rowptr_g[lo]).contiguous()
         nnz = int(rowptr[-1]) if hi > lo else 0
@@ -155,21 +169,18 @@ class ShardedElphHashes(object):
         device = edge_index.device if edge_index.is_cuda else torch.device('cuda', torch.cuda.current_device())
         K = eh.max_hops
         with torch.cuda.device(device):
-            ev = eh._event_begin(device)
-            rowptr, colidx, nnz, bounds = self._local_csr(edge_index, num_nodes, device)
-            eh._event_end('csr_build', ev, device)
-            self.bounds, self.local_nnz = bounds, nnz
-            lo, hi = bounds[r], bounds[r + 1]
             rb = eh._record_bytes()
             symm = None
             if self.exchange in ('auto', 'p2p'):
                 symm = self._symmetric_buffers(num_nodes, K, rb, device)
                 if symm is None and self.exchange == 'p2p':
                     raise RuntimeError(f'symmetric memory is unavailable: {self.exchange_error}')
-                if symm is None:
-                    self.exchange = 'nccl'
-                else:
-                    self.exchange = 'p2p'
+                self.exchange = 'nccl' if symm is None else 'p2p'
+            ev = eh._event_begin(device)
+            rowptr, colidx, nnz, bounds = self._local_csr(edge_index, num_nodes, device)
+            eh._event_end('csr_build', ev, device)
+            self.bounds, self.local_nnz = bounds, nnz
+            lo, hi = bounds[r], bounds[r + 1]
             rec0 = torch.empty((num_nodes, rb), dtype=torch.uint8, device=device)
             ev = eh._event_begin(device)
             eh._init_records(num_nodes, device, out=rec0)  # hop 0 is cheap: computed redundantly, no exchange

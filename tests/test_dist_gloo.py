@@ -42,6 +42,10 @@ def test_balanced_bounds_split_neighbours_evenly():
         shares = [int(rowptr[b[r + 1]] - rowptr[b[r]]) for r in range(G)]
         assert sum(shares) == nnz
         assert max(shares) <= nnz / G + int(deg.max()), (G, shares)
+        bw = balanced_bounds(rowptr, G, row_weight=50.0)  # row-dominated cost -> nearly equal row blocks
+        assert bw[0] == 0 and bw[-1] == 5000 and all(x <= y for x, y in zip(bw, bw[1:]))
+        if G > 1:
+            assert bw[1] > b[1]
     assert balanced_bounds(torch.zeros(1, dtype=torch.long), 4) == [0, 0, 0, 0, 0]
     assert balanced_bounds(torch.zeros(6, dtype=torch.long), 2)[-1] == 5
 
