@@ -26,15 +26,6 @@ struct LinkArgs {
     RecordShape s;
 };
 
-// ---- per-combination statistics of the union sketch, default shape ---------------------------------
-// Fast path: every register <= 28, so sum 2^-r fits a 32-bit fixed-point lane accumulator in units of 2^-28
-// (8 registers per lane, each <= 2^28).  Otherwise the exact 64-bit accumulator is used.  Both give the
-// exactly rounded float32 of the true sum.
-__device__ __forceinline__ uint32_t sum_pow_word28(uint32_t w) {
-    return (0x10000000u >> (w & 0xffu)) + (0x10000000u >> ((w >> 8) & 0xffu)) + (0x10000000u >> ((w >> 16) & 0xffu)) +
-           (0x10000000u >> (w >> 24));
-}
-
 // scalar tail: (zeros, S = sum 2^-r as float, matches) -> jaccard * union cardinality (hashing.py:184-187)
 __device__ __forceinline__ float intersection_tail(const HllDev &h, int zeros, float S, uint32_t matches, int P) {
     float val = __fadd_rn(h.threshold, 1.0f);
@@ -106,9 +97,42 @@ __device__ __forceinline__ void knockout_and_floor(float *f, int flags) {
 }
 
 // ---- default shape (P=128, p=8): one warp per link, records in registers ----------------------------
+// Per record a lane keeps: 4 MinHash slots, its 8 HLL registers split into an even-byte and an odd-byte plane
+// (two 16-bit lanes per word, so the union max is the native VIMNMX.U16x2 -- a 4 x uint8 max costs 7
+// instructions), and an 8-bit non-zero mask.  Per combination: 4 compares, 4 maxes, 8 funnel shifts for
+// sum 2^-r (shf.r.wrap needs no byte extraction for the low byte of a 16-bit lane), one popc for the zero
+// count.  Match counts and zero counts of all K^2 combinations are packed into bit fields and reduced across
+// the warp once per word instead of once per combination.
+struct RowRegs {
+    uint4 mh;
+    uint2 he, ho;   // even / odd byte planes of the lane's 8 HLL registers
+    uint32_t nz;    // bit set per non-zero register (bits 7,15,23,31 from word x; 6,14,22,30 from word y)
+};
+
+__device__ __forceinline__ void prep_row(RowRegs &r, const uint4 &m, const uint2 &h, uint32_t &big) {
+    r.mh = m;
+    r.he = make_uint2(h.x & 0x00ff00ffu, h.y & 0x00ff00ffu);
+    r.ho = make_uint2(h.x & 0xff00ff00u, h.y & 0xff00ff00u);
+    const uint32_t nzx = ((h.x + 0x7f7f7f7fu) | h.x) & 0x80808080u;
+    const uint32_t nzy = ((h.y + 0x7f7f7f7fu) | h.y) & 0x80808080u;
+    r.nz = nzx | (nzy >> 1);
+    big |= (((h.x + 0x63636363u) | h.x) | ((h.y + 0x63636363u) | h.y)) & 0x80808080u;  // any register > 28
+}
+
+// sum over the two 16-bit lanes of an even-plane word (register value in the LOW byte of each lane) of
+// 2^(28 - r); shf.r.wrap uses only the low 5 bits of the shift amount
+__device__ __forceinline__ uint32_t pow_sum_even(uint32_t w) {
+    return __funnelshift_r(0x10000000u, 0u, w) + __funnelshift_r(0x10000000u, 0u, w >> 16);
+}
+// same for an odd-plane word (register value in the HIGH byte of each lane)
+__device__ __forceinline__ uint32_t pow_sum_odd(uint32_t w) {
+    return __funnelshift_r(0x10000000u, 0u, w >> 8) + __funnelshift_r(0x10000000u, 0u, w >> 24);
+}
+
 template <int K>
-__global__ void __launch_bounds__(256) link_features_kernel(const LinkArgs a) {
+__global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a) {
     constexpr int F = K * (K + 2);
+    constexpr int C = K * K;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -131,52 +155,67 @@ __global__ void __launch_bounds__(256) link_features_kernel(const LinkArgs a) {
             cu[k] = __ldg(a.cards + u * a.cards_stride + k);
             cv[k] = __ldg(a.cards + v * a.cards_stride + k);
         }
-        // combination c = (k1-1)*K + (k2-1) ends up on lane c: (zeros, S, matches)
+        RowRegs U[K], V[K];
+        uint32_t big = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            prep_row(U[k], mu[k], hu[k], big);
+            prep_row(V[k], mv[k], hv[k], big);
+        }
+        const bool any_big = __any_sync(FULL, big != 0u);  // rare: some register > 28 -> exact 128-bit path
+
+        // per-lane partial statistics of every combination c = (k1-1)*K + (k2-1)
+        uint32_t eq_pack[(C + 3) / 4] = {0};   // 8-bit fields: matches per lane <= 4, per warp <= 128
+        uint32_t nz_pack[(C + 2) / 3] = {0};   // 10-bit fields: non-zero registers per lane <= 8, per warp <= 256
         int my_zeros = 0;
         float my_S = 1.f;
-        uint32_t my_match = 0;
 #pragma unroll
         for (int k1 = 0; k1 < K; ++k1) {
 #pragma unroll
             for (int k2 = 0; k2 < K; ++k2) {
-                uint32_t eq = (mu[k1].x == mv[k2].x) + (mu[k1].y == mv[k2].y) + (mu[k1].z == mv[k2].z) +
-                              (mu[k1].w == mv[k2].w);
-                const uint32_t wx = __vmaxu4(hu[k1].x, hv[k2].x), wy = __vmaxu4(hu[k1].y, hv[k2].y);
-                const uint32_t big = (((wx + 0x63636363u) | wx) | ((wy + 0x63636363u) | wy)) & 0x80808080u;  // any register > 28
-                int zeros;
+                const int c = k1 * K + k2;
+                const uint32_t eq = (U[k1].mh.x == V[k2].mh.x) + (U[k1].mh.y == V[k2].mh.y) +
+                                    (U[k1].mh.z == V[k2].mh.z) + (U[k1].mh.w == V[k2].mh.w);
+                eq_pack[c / 4] += eq << (8 * (c % 4));
+                nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
+                const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
+                const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
                 float S;
-                if (!__any_sync(FULL, big != 0u)) {
-                    const uint32_t nzx = (wx + 0x7f7f7f7fu) & 0x80808080u, nzy = (wy + 0x7f7f7f7fu) & 0x80808080u;
-                    const uint32_t acc = sum_pow_word28(wx) + sum_pow_word28(wy);  // <= 2^31
-                    // pack: zeros (<= 8 per lane) ride in the low-half reduction's spare bits
+                if (!any_big) {
+                    const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_odd(ox) + pow_sum_odd(oy);  // <= 2^31
                     const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
                     const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
-                    const uint32_t nz = __reduce_add_sync(FULL, (uint32_t)(__popc(nzx) + __popc(nzy)));
-                    zeros = 256 - (int)nz;
                     const uint64_t total = (uint64_t)lo + ((uint64_t)hi << 16);
                     S = __fmul_rn(__ull2float_rn(total), 3.7252902984619140625e-09f);  // * 2^-28, exact
                 } else {
                     uint64_t acc = 0;
-                    int nz = 0;
-                    acc_regs_word(wx, acc, nz);
-                    acc_regs_word(wy, acc, nz);
+                    int nz = 0, zeros;
+                    acc_regs_word(ex | ox, acc, nz);
+                    acc_regs_word(ey | oy, acc, nz);
                     unsigned __int128 t = warp_total_units(acc, nz, zeros);
                     S = units_to_f32(t);
+                    if (lane == c) my_zeros = zeros;
                 }
-                eq = __reduce_add_sync(FULL, eq);
-                if (lane == k1 * K + k2) {
-                    my_zeros = zeros;
-                    my_S = S;
-                    my_match = eq;
-                }
+                if (lane == c) my_S = S;
             }
         }
-        float my_inter = 0.f;
-        if (lane < K * K) my_inter = intersection_tail(a.h, my_zeros, my_S, my_match, 128);
-        float I[K * K];
+        uint32_t my_match = 0;
 #pragma unroll
-        for (int c = 0; c < K * K; ++c) I[c] = __shfl_sync(FULL, my_inter, c);
-        if (a.inter && lane < K * K) a.inter[i * (K * K) + lane] = my_inter;
+        for (int w = 0; w < (C + 3) / 4; ++w) {
+            const uint32_t r = __reduce_add_sync(FULL, eq_pack[w]);
+            if (lane / 4 == w) my_match = (r >> (8 * (lane % 4))) & 0xffu;
+        }
+#pragma unroll
+        for (int w = 0; w < (C + 2) / 3; ++w) {
+            const uint32_t r = __reduce_add_sync(FULL, nz_pack[w]);
+            if (lane / 3 == w && !any_big) my_zeros = 256 - (int)((r >> (10 * (lane % 3))) & 0x3ffu);
+        }
+        float my_inter = 0.f;
+        if (lane < C) my_inter = intersection_tail(a.h, my_zeros, my_S, my_match, 128);
+        float I[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, c);
+        if (a.inter && lane < C) a.inter[i * C + lane] = my_inter;
         if (a.features) {
             float f[F];
             feature_algebra<K>(I, cu, cv, f);
