@@ -131,19 +131,31 @@ def log2_window_table():
 
 
 class _CsrCache(object):
-    """destination-keyed CSR of one edge_index, cached on identity so that ELPH's per-batch
-    hll_prop/minhash_prop calls (models/elph.py:209-212) build it once"""
+    """destination-keyed CSR of the most recent edge_index, so that ELPH's per-batch hll_prop / minhash_prop
+    calls (models/elph.py:209-212: 2K calls per forward, same graph every batch) build it once.  The key is
+    the tensor's shape plus a content fingerprint computed on the device -- ELPH creates a fresh
+    `add_self_loops` tensor on every forward (often at a recycled address), so identity is not a safe key."""
 
     def __init__(self):
         self.key = None
         self.value = None
 
+    @staticmethod
+    def fingerprint(ei):
+        if ei.shape[1] == 0:
+            return (0, 0)
+        a = ei[0] * 1000003 + ei[1]
+        n = ei.shape[1]
+        return (int(a.sum()), int((a[:: max(n // 64, 1)] * torch.arange(1, a[:: max(n // 64, 1)].numel() + 1,
+                                                                        device=ei.device)).sum()))
+
     def get(self, edge_index, device, add_loops):
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(device), add_loops)
-        if key == self.key:
-            return self.value
-        self.value = build_csr(edge_index, device, add_loops=add_loops)
-        self.key = key
+        ei = _to_device(edge_index, device)
+        ei = (ei if ei.dtype == torch.int64 else ei.long()).contiguous()
+        key = (tuple(ei.shape), str(device), add_loops, self.fingerprint(ei))
+        if key != self.key:
+            self.value = build_csr(ei, device, add_loops=add_loops)
+            self.key = key
         return self.value
 
 
@@ -177,8 +189,8 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0):
 class MinhashPropagation(object):
     """element-wise min over in-neighbours (hashing.py:28-35).  `edge_index` already holds the self loops."""
 
-    def __init__(self, owner=None):
-        self._csr = _CsrCache()
+    def __init__(self, csr_cache=None):
+        self._csr = csr_cache if csr_cache is not None else _CsrCache()
 
     @torch.no_grad()
     def __call__(self, x, edge_index):
@@ -192,8 +204,8 @@ class MinhashPropagation(object):
 class HllPropagation(object):
     """register-wise max over in-neighbours (hashing.py:38-45)"""
 
-    def __init__(self, owner=None):
-        self._csr = _CsrCache()
+    def __init__(self, csr_cache=None):
+        self._csr = csr_cache if csr_cache is not None else _CsrCache()
 
     @torch.no_grad()
     def __call__(self, x, edge_index):
@@ -308,7 +320,8 @@ class ElphHashes(object):
         self._minhash_range = (1 << 32)
         self.minhash_seed = 1
         self.num_perm = args.minhash_num_perm
-        self.minhash_prop = MinhashPropagation()
+        self._csr_cache = _CsrCache()  # shared by both operators
+        self.minhash_prop = MinhashPropagation(self._csr_cache)
         # hll params (hashing.py:64-81)
         self.p = args.hll_p
         self.m = 1 << self.p
@@ -326,7 +339,7 @@ class ElphHashes(object):
         self.hll_threshold = threshold
         self.bias_vector = torch.tensor(np.asarray(bias, dtype=np.float64), dtype=torch.float)
         self.estimate_vector = torch.tensor(np.asarray(raw_estimate, dtype=np.float64), dtype=torch.float)
-        self.hll_prop = HllPropagation()
+        self.hll_prop = HllPropagation(self._csr_cache)
         self.merge_variant = merge_variant
         self.validate_links = True  # bounds-check link endpoints (the reference raises IndexError)
         self.event_log = None  # set to a list to record (name, start_event, end_event) around kernels

@@ -318,3 +318,43 @@ def test_empty_and_degenerate_inputs():
     assert int(tables[1]['minhash'][2].abs().sum()) == 0
     with pytest.raises(IndexError):
         eh.build_hash_tables(3, torch.tensor([[0, 5], [1, 0]], device=DEV))
+
+
+def test_elph_forward_call_pattern():
+    """the exact engine call sequence of ELPH.forward + train_elph (models/elph.py:186-213, train.py:198-204):
+    hop-0 sketches moved to the device, add_self_loops'd edge_index rebuilt on every forward, per-hop
+    hll_prop / minhash_prop / hll_count into a CPU `cards`, then get_subgraph_features on a plain dict of
+    int64 / int8 CUDA tensors."""
+    n, K = 3000, 2
+    g = torch.Generator().manual_seed(21)
+    ei = torch.randint(0, n - 50, (2, 20000), generator=g)
+    links = torch.randint(0, n, (2048, 2), generator=g)
+    o = so.OracleSketches(K, 128, 8, use_zero_one=False, floor_sf=False)
+    ot, oc = o.build_hash_tables(n, ei)
+    of = o.subgraph_features(links, ot, oc)
+    eh = ssb.ElphHashes(make_args(K))
+    ei_d = ei.to(DEV)
+    init_hashes = eh.initialise_minhash(n).to(DEV)
+    init_hll = eh.initialise_hll(n).to(DEV)
+    for forward_call in range(2):  # second call hits the CSR cache although the loop tensor is a new object
+        hash_edge_index = so.with_self_loops(ei_d)
+        cards = torch.zeros((n, K))
+        table = {}
+        for k in range(K + 1):
+            if k == 0:
+                table[k] = {'minhash': init_hashes, 'hll': init_hll}
+            else:
+                table[k] = {'hll': eh.hll_prop(table[k - 1]['hll'], hash_edge_index),
+                            'minhash': eh.minhash_prop(table[k - 1]['minhash'], hash_edge_index)}
+                cards[:, k - 1] = eh.hll_count(table[k]['hll'])
+        for k in range(K + 1):
+            assert torch.equal(table[k]['minhash'].cpu(), ot[k]['minhash'])
+            assert torch.equal(table[k]['hll'].cpu(), ot[k]['hll'])
+        feats = eh.get_subgraph_features(links.to(DEV), table, cards)
+        assert feats.is_cuda
+        ok, err = float_close(feats.cpu(), of, link_scale(links, oc))
+        assert ok, err
+    # a different graph of the same shape must not be served from the cache
+    ei2 = torch.randint(0, n - 50, (2, 20000), generator=g).to(DEV)
+    h2 = eh.hll_prop(init_hll, so.with_self_loops(ei2))
+    assert torch.equal(h2.cpu(), so.hll_propagate(init_hll.cpu(), so.with_self_loops(ei2.cpu())))
