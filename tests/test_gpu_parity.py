@@ -358,3 +358,67 @@ def test_elph_forward_call_pattern():
     ei2 = torch.randint(0, n - 50, (2, 20000), generator=g).to(DEV)
     h2 = eh.hll_prop(init_hll, so.with_self_loops(ei2))
     assert torch.equal(h2.cpu(), so.hll_propagate(init_hll.cpu(), so.with_self_loops(ei2.cpu())))
+
+
+def test_full_size_properties_rmat24():
+    """BASELINE.json's scaling-sweep size (R-MAT scale 24, 16.8 M nodes, ~537 M neighbours, K=3) through
+    size-independent properties: engine-vs-engine checksum of whole tables, sampled rows against a direct
+    gather-reduce, hop monotonicity (self loops), cards == hll_count(table), intersection symmetry."""
+    import os
+    scale = int(os.environ.get('SS_TEST_FULL_SCALE', '24'))
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9 * (1 << scale) / (1 << 24):
+        pytest.skip('not enough free device memory for the full-size case')
+    n, K = 1 << scale, 3
+    dev = torch.device(DEV)
+    ei = rmat_edges(scale, 16, 0, dev)
+    eh = ssb.ElphHashes(make_args(K))
+    tables, cards = eh.build_hash_tables(n, ei)
+    rowptr, colidx, nnz, _ = ssb.build_csr(ei, dev, num_rows=n, add_loops=True)
+    del ei
+    # (1) checksum of checksums: the per-row bulk-copy engine must reproduce the gather4 engine bit for bit
+    alt = ssb.ElphHashes(make_args(K), merge_variant='bulk')
+    out = torch.empty_like(tables.records(1))
+    c2 = torch.zeros((n, 1), device=dev)
+    for k in (1, 2):
+        alt._merge(rowptr, colidx, nnz, tables.records(k - 1), out, c2[:, 0], dev)
+        assert int(out.view(torch.int32).sum(dtype=torch.int64)) == int(tables.records(k).view(torch.int32).sum(dtype=torch.int64))
+        assert torch.equal(c2[:, 0], cards[:, k - 1])
+    assert torch.equal(out, tables.records(2))
+    del out
+    # (2) sampled rows (hubs included) against a direct gather + min/max in torch
+    g = torch.Generator().manual_seed(0)
+    deg = rowptr[1:] - rowptr[:-1]
+    sample = torch.cat([torch.randint(0, n, (300,), generator=g).to(dev), torch.topk(deg, 3).indices])
+    for k in (1, 3):
+        prev = tables.records(k - 1)
+        for r in sample.tolist():
+            nb = colidx[int(rowptr[r]):int(rowptr[r + 1])].long()
+            rows = prev[nb]
+            want_mh = rows[:, :512].contiguous().view(torch.int32).long().bitwise_and(0xffffffff).min(dim=0).values
+            want_hl = rows[:, 512:].max(dim=0).values
+            got = tables.records(k)[r]
+            assert torch.equal(got[:512].view(torch.int32).long().bitwise_and(0xffffffff), want_mh), (k, r)
+            assert torch.equal(got[512:], want_hl), (k, r)
+    # (3) hop monotonicity on a row sample: every node has a self loop, so sketches only grow
+    # (nodes above max(edge_index) get no self loop -- quirk 8a-Q4 -- and are all-zero from hop 1 on)
+    max_id = int(colidx[:nnz].max())
+    idx = torch.randint(0, max_id + 1, (200000,), generator=g).to(dev)
+    if max_id + 1 < n:
+        assert int(tables.records(1)[max_id + 1:].count_nonzero()) == 0
+    for k in (1, 2, 3):
+        a, b = tables.records(k - 1)[idx], tables.records(k)[idx]
+        mh_a = a[:, :512].contiguous().view(torch.int32).long().bitwise_and(0xffffffff)
+        mh_b = b[:, :512].contiguous().view(torch.int32).long().bitwise_and(0xffffffff)
+        assert bool((mh_b <= mh_a).all()) and bool((b[:, 512:] >= a[:, 512:]).all())
+        # (4) cards[:, k-1] == hll_count(table[k].hll) on the sample (test_hashing.py:216-227 at full size)
+        assert torch.equal(eh.hll_count(b[:, 512:].contiguous()), cards[idx, k - 1])
+    # (5) intersection symmetry on 1 M links
+    links = torch.randint(0, n, (1_000_000, 2), generator=g).to(dev)
+    ia = eh._get_intersections(links, tables)
+    ib = eh._get_intersections(links.flip(1), tables)
+    for k1 in (1, 2, 3):
+        for k2 in (1, 2, 3):
+            assert torch.equal(ia[(k1, k2)], ib[(k2, k1)])
+    f = eh.get_subgraph_features(links, tables, cards)
+    assert f.shape == (1_000_000, 15) and bool(torch.isfinite(f).all())
