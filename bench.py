@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_OUT = sys.stdout
 METRIC = 'link structural features/sec'
 UNIT = 'links/s'
 
@@ -191,11 +192,16 @@ def run_reference(a, spec):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
+    # the contract is ONE JSON line on stdout: keep a private handle to the real stdout and send everything
+    # else that writes to fd 1 (NCCL's version banner, library chatter) to stderr
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     a = parse()
     spec = workload_spec(a)
     if a.impl == 'reference':
@@ -368,7 +374,7 @@ def main():
             'roofline': roofline, 'link_features_roofline': link_roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e,
             'gpu_launches': launches, 'clocks': clocks,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if distributed:
         dist.destroy_process_group()
 

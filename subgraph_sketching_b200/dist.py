@@ -46,22 +46,27 @@ def link_slice(n_links, world_size, rank):
     return lo, min(lo + per, n_links)
 
 
-def balanced_bounds(rowptr, world_size, row_weight=0.0):
-    """row boundaries [b_0 = 0, ..., b_G = N] such that every block carries the same COST
-    cost(block) = neighbours(block) + row_weight * rows(block).
+def balanced_bounds(rowptr, world_size, row_weight=0.0, shares=None):
+    """row boundaries [b_0 = 0, ..., b_G = N] such that block r carries the fraction shares[r] (default 1/G)
+    of the total COST, cost(block) = neighbours(block) + row_weight * rows(block).
     One neighbour = one 768-byte gather from HBM; a finished row costs one local store plus, in the fused p2p
-    exchange, one 768-byte store per peer over NVLink (about 10x the time of an HBM gather), so the row term
-    dominates at 8 GPUs and vanishes at 1.  `rowptr` is the global int64 [N + 1] prefix sum (any device);
-    returns a python list of G + 1 ints."""
+    exchange, one 768-byte store per peer over NVLink, so the row term dominates at 8 GPUs and vanishes at 1.
+    `rowptr` is the global int64 [N + 1] prefix sum (any device); returns a python list of G + 1 ints."""
     n = rowptr.numel() - 1
     if n <= 0:
         return [0] * (world_size + 1)
     if world_size == 1:
         return [0, n]
+    if shares is None:
+        shares = [1.0 / world_size] * world_size
+    tot_share = float(sum(shares))
+    cum, acc = [], 0.0
+    for r in range(world_size - 1):
+        acc += float(shares[r]) / tot_share
+        cum.append(acc)
     cost = rowptr.double() + float(row_weight) * torch.arange(n + 1, device=rowptr.device, dtype=torch.float64)
     total = float(cost[-1])
-    targets = torch.tensor([total * r / world_size for r in range(1, world_size)], dtype=torch.float64,
-                           device=rowptr.device)
+    targets = torch.tensor([total * c for c in cum], dtype=torch.float64, device=rowptr.device)
     cuts = torch.searchsorted(cost, targets, right=False).clamp_(0, n).tolist()
     bounds = [0] + [int(c) for c in cuts] + [n]
     for i in range(1, len(bounds)):  # monotone, in range
@@ -104,6 +109,11 @@ class ShardedElphHashes(object):
         self.local_nnz = None
         self.exchange = exchange
         self._symm = None       # cached symmetric buffers: (key, recs[1..K], cards, handles)
+        # adaptive balance: the share of the total cost each rank gets follows its measured merge throughput
+        # in the previous build (ranks differ in L2 hit rate and NVLink egress, which no static model captures)
+        self.adaptive = True
+        self.shares = None
+        self._merge_events = []
         self.exchange_error = None
         if self.world_size == 1 or self.world_size - 1 > 7:
             self.exchange = 'nccl'
@@ -153,7 +163,8 @@ class ShardedElphHashes(object):
         st = _stream_ptr(device)
         check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, n_loops, 0, num_nodes, _ptr(rowptr_g), _ptr(ws),
                                 ws.numel(), st), 'ss_csr_rowptr')
-        bounds = balanced_bounds(rowptr_g, self.world_size, default_row_weight(self.world_size, self.exchange))
+        bounds = balanced_bounds(rowptr_g, self.world_size, default_row_weight(self.world_size, self.exchange),
+                                 self.shares)
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
         rowptr = (rowptr_g[lo:hi + 1] - rowptr_g[lo]).contiguous()
         nnz = int(rowptr[-1]) if hi > lo else 0
@@ -163,12 +174,31 @@ class ShardedElphHashes(object):
                                   _ptr(ws), ws.numel(), st), 'ss_csr_fill')
         return rowptr, colidx, nnz, bounds
 
+    def _update_shares(self, device):
+        """turn the merge times of the previous build into new cost shares (one tiny all-gather)"""
+        if not self.adaptive or self.world_size == 1 or not self._merge_events:
+            return
+        ms = sum(s.elapsed_time(e) for s, e in self._merge_events)  # events of a finished build: no stall
+        self._merge_events = []
+        mine = torch.tensor([ms], device=device, dtype=torch.float64)
+        allms = torch.empty(self.world_size, device=device, dtype=torch.float64)
+        dist.all_gather_into_tensor(allms, mine, group=self.group)
+        t = allms.clamp_(min=1e-3).tolist()
+        old = self.shares or [1.0 / self.world_size] * self.world_size
+        # throughput of rank r = share_r / t_r; next shares proportional to it (damped)
+        speed = [o / x for o, x in zip(old, t)]
+        tot = sum(speed)
+        new = [0.5 * o + 0.5 * (v / tot) for o, v in zip(old, speed)]
+        tot = sum(new)
+        self.shares = [v / tot for v in new]
+
     def build_hash_tables(self, num_nodes, edge_index):
         eh, r = self.eh, self.rank
         _lib.require_cuda()
         device = edge_index.device if edge_index.is_cuda else torch.device('cuda', torch.cuda.current_device())
         K = eh.max_hops
         with torch.cuda.device(device):
+            self._update_shares(device)
             rb = eh._record_bytes()
             symm = None
             if self.exchange in ('auto', 'p2p'):
@@ -195,8 +225,13 @@ class ShardedElphHashes(object):
                     if hi > lo:
                         peer_recs = [int(hdls[k - 1].buffer_ptrs[q]) + lo * rb for q in others]
                         peer_cards = [int(chdl.buffer_ptrs[q]) + (lo * K + (k - 1)) * 4 for q in others]
+                        t0 = torch.cuda.Event(enable_timing=True)
+                        t0.record()
                         ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
                                        ws, peer_recs, peer_cards)
+                        t1 = torch.cuda.Event(enable_timing=True)
+                        t1.record()
+                        self._merge_events.append((t0, t1))
                     ev = eh._event_begin(device)
                     hdls[k - 1].barrier()  # every rank's launch (and its peer stores) has completed
                     eh._event_end('exchange', ev, device)
@@ -205,8 +240,13 @@ class ShardedElphHashes(object):
                 cards = torch.zeros((num_nodes, K), dtype=torch.float32, device=device)
                 for k in range(1, K + 1):
                     if hi > lo:
+                        t0 = torch.cuda.Event(enable_timing=True)
+                        t0.record()
                         ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
                                        ws)
+                        t1 = torch.cuda.Event(enable_timing=True)
+                        t1.record()
+                        self._merge_events.append((t0, t1))
                     ev = eh._event_begin(device)
                     exchange_blocks(recs[k], bounds, self.group)
                     eh._event_end('exchange', ev, device)
