@@ -47,7 +47,7 @@ def parse():
     ap.add_argument('--ref-scale', type=int, default=15, help='R-MAT scale of each --impl reference step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'nccl'], help='multi-GPU exchange mode')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'mc', 'nccl'], help='multi-GPU exchange mode')
     ap.add_argument('--seed', type=int, default=0)
     return ap.parse_args()
 

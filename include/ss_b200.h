@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 4
+#define SS_ABI_VERSION 5
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -148,13 +148,16 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
  * are HOST arrays of device pointers addressed exactly like rec_out / cards_out (row 0 = first owned row).
  * When every rank's launch has completed (stream-ordered barrier between ranks), every rank holds the whole
  * next-hop table: the per-hop all-gather of the sketches happens inside the kernel, overlapped row by row.
- * P=128 / p=8 engines only. */
+ * mc_rec_out / mc_cards_out (optional, else NULL): NVSwitch MULTICAST addresses of the same buffers
+ * (cuMulticast / symmetric memory `multicast_ptr`), addressed like rec_out / cards_out; when given, every
+ * store is ONE `multimem.st` that the switch replicates into all GPUs' copies (the writer's included) and the
+ * peer arrays are ignored.  P=128 / p=8 engines only. */
 #define SS_MAX_PEERS 7
 int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
                         int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p,
                         void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
                         const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
-                        float *const *peer_cards_out, ss_stream_t stream);
+                        float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, ss_stream_t stream);
 
 /* operator forms on the reference's own tensor layouts (ELPH calls these per batch,
  * /root/reference/src/models/elph.py:209-212): element-wise signed min (int64) / max (int8) over

@@ -53,6 +53,9 @@ struct MergeArgs {
     int n_peers;
     uint8_t *peer_out[SS_MAX_PEERS];
     float *peer_cards[SS_MAX_PEERS];
+    // NVSwitch multicast alternative: ONE multimem.st per store lands in every GPU's copy (own copy included)
+    uint8_t *mc_out;
+    float *mc_cards;
 };
 
 // HLL++ estimate of a row held as 8 registers per lane.  Not inlined: it is called once per output row
@@ -75,20 +78,44 @@ __device__ __noinline__ float row_cardinality(uint2 hl, int m, int T, int monoto
     row_cardinality(hl, (a).h.m, (a).h.T, (a).h.monotone, (a).h.threshold, (a).h.alpha_m2, (a).h.five_m, (a).h.lc, \
                     (a).h.est, (a).h.bias)
 
+__device__ __forceinline__ void mc_st_u4(void *p, const uint4 &v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+__device__ __forceinline__ void mc_st_u2(void *p, const uint2 &v) {
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y))
+                 : "memory");
+}
+__device__ __forceinline__ void mc_st_f32(float *p, float v) {
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // final store of output row `row`: local table, its cardinality, and the same to every peer table
+// (one store per peer over NVLink, or one multicast store that the NVSwitch replicates to every GPU)
 __device__ __forceinline__ void store_row(const MergeArgs &a, int64_t row, const uint4 &mh, const uint2 &hl, int lane) {
     const int64_t off = row * a.out_stride;
-    st_na_u4(a.out + off + lane * 16, mh);
-    st_na_u2(a.out + off + REC_MH + lane * 8, hl);
-    for (int p = 0; p < a.n_peers; ++p) {
-        st_na_u4(a.peer_out[p] + off + lane * 16, mh);
-        st_na_u2(a.peer_out[p] + off + REC_MH + lane * 8, hl);
+    if (a.mc_out) {
+        mc_st_u4(a.mc_out + off + lane * 16, mh);
+        mc_st_u2(a.mc_out + off + REC_MH + lane * 8, hl);
+    } else {
+        st_na_u4(a.out + off + lane * 16, mh);
+        st_na_u2(a.out + off + REC_MH + lane * 8, hl);
+        for (int p = 0; p < a.n_peers; ++p) {
+            st_na_u4(a.peer_out[p] + off + lane * 16, mh);
+            st_na_u2(a.peer_out[p] + off + REC_MH + lane * 8, hl);
+        }
     }
     if (a.cards) {
         float c = ROW_CARD(a, hl);
         if (lane == 0) {
-            a.cards[row * a.cards_stride] = c;
-            for (int p = 0; p < a.n_peers; ++p) a.peer_cards[p][row * a.cards_stride] = c;
+            if (a.mc_cards) {
+                mc_st_f32(a.mc_cards + row * a.cards_stride, c);
+            } else {
+                a.cards[row * a.cards_stride] = c;
+                for (int p = 0; p < a.n_peers; ++p) a.peer_cards[p][row * a.cards_stride] = c;
+            }
         }
     }
 }
@@ -677,14 +704,15 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
                   int64_t workspace_bytes, float *cards_out, int64_t cards_stride, const ss_hll_consts *hc, int variant,
                   ss_stream_t stream) {
     return ss_khop_merge_peers(rowptr, colidx, n_rows, nnz, rec_in, in_rows, in_stride, rec_out, out_stride, num_perm, hll_p,
-                               workspace, workspace_bytes, cards_out, cards_stride, hc, variant, 0, nullptr, nullptr, stream);
+                               workspace, workspace_bytes, cards_out, cards_stride, hc, variant, 0, nullptr, nullptr, nullptr,
+                               nullptr, stream);
 }
 
 int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
                         int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p,
                         void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
                         const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
-                        float *const *peer_cards_out, ss_stream_t stream) {
+                        float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n_rows >= 0 && nnz >= 0 && in_rows >= 0, "negative size passed to ss_khop_merge");
@@ -712,6 +740,7 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
     SS_REQUIRE(n_peers >= 0 && n_peers <= SS_MAX_PEERS, "n_peers must be in [0, %d]", SS_MAX_PEERS);
     SS_REQUIRE(n_peers == 0 || (variant != SS_MERGE_GENERIC && peer_rec_out && (!cards_out || peer_cards_out)),
                "peer stores need the P=128/p=8 engines and one pointer per peer");
+    SS_REQUIRE(!mc_rec_out || variant != SS_MERGE_GENERIC, "multicast stores need the P=128/p=8 engines");
     if (variant == SS_MERGE_GENERIC) {
         ss::GenericArgs g;
         g.rowptr = rowptr; g.colidx = colidx; g.n_rows = n_rows;
@@ -733,6 +762,10 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
     a.n_ranges = ss::n_ranges_for(nnz, a.quantum);
     a.scratch = (uint8_t *)workspace;
     a.cards = cards_out; a.cards_stride = cards_stride; a.h = hd;
+    SS_REQUIRE(!mc_rec_out || (((uintptr_t)mc_rec_out & 15) == 0 && (!cards_out || mc_cards_out)),
+               "multicast table must be 16-byte aligned and come with a multicast cards pointer");
+    a.mc_out = (uint8_t *)mc_rec_out;
+    a.mc_cards = mc_rec_out ? mc_cards_out : nullptr;
     a.n_peers = n_peers;
     for (int p = 0; p < SS_MAX_PEERS; ++p) {
         a.peer_out[p] = p < n_peers ? (uint8_t *)peer_rec_out[p] : nullptr;

@@ -18,6 +18,8 @@ Exchange modes
          and the merge kernel itself stores each finished row into all peer tables (ss_khop_merge_peers), so
          the exchange is fused into the kernel and overlaps the merge row by row; a stream-ordered
          symmetric-memory barrier separates the hops.  No NCCL call on the data path.
+  'mc'   like 'p2p', but every store is ONE multimem.st to the NVSwitch multicast address of the buffer: the
+         switch replicates the row into all GPUs' tables, so a GPU sends each row once instead of G-1 times.
   'nccl' one torch.distributed broadcast per owner block after the merge kernel (works everywhere).
 
 The reference has no distributed code at all (src/hashing.py is single process); results are bit-identical
@@ -100,7 +102,7 @@ class ShardedElphHashes(object):
     (`link_slice`)."""
 
     def __init__(self, args, group=None, exchange='auto', **kw):
-        assert exchange in ('auto', 'p2p', 'nccl')
+        assert exchange in ('auto', 'p2p', 'mc', 'nccl')
         self.eh = ElphHashes(args, **kw)
         self.group = group
         self.world_size = dist.get_world_size(group)
@@ -201,11 +203,16 @@ class ShardedElphHashes(object):
             self._update_shares(device)
             rb = eh._record_bytes()
             symm = None
-            if self.exchange in ('auto', 'p2p'):
+            if self.exchange in ('auto', 'p2p', 'mc'):
                 symm = self._symmetric_buffers(num_nodes, K, rb, device)
-                if symm is None and self.exchange == 'p2p':
+                if symm is None and self.exchange in ('p2p', 'mc'):
                     raise RuntimeError(f'symmetric memory is unavailable: {self.exchange_error}')
-                self.exchange = 'nccl' if symm is None else 'p2p'
+                if symm is None:
+                    self.exchange = 'nccl'
+                elif self.exchange == 'auto':
+                    self.exchange = 'p2p'
+                if self.exchange == 'mc' and not all(int(h.multicast_ptr) for h in list(symm[3]) + [symm[4]]):
+                    raise RuntimeError('this system has no NVSwitch multicast support for symmetric memory')
             ev = eh._event_begin(device)
             rowptr, colidx, nnz, bounds = self._local_csr(edge_index, num_nodes, device)
             eh._event_end('csr_build', ev, device)
@@ -223,12 +230,18 @@ class ShardedElphHashes(object):
                 hdls[0].barrier()  # no peer still reads these buffers from an earlier build
                 for k in range(1, K + 1):
                     if hi > lo:
-                        peer_recs = [int(hdls[k - 1].buffer_ptrs[q]) + lo * rb for q in others]
-                        peer_cards = [int(chdl.buffer_ptrs[q]) + (lo * K + (k - 1)) * 4 for q in others]
+                        mc_rec = mc_cards = 0
+                        peer_recs = peer_cards = None
+                        if self.exchange == 'mc':
+                            mc_rec = int(hdls[k - 1].multicast_ptr) + lo * rb
+                            mc_cards = int(chdl.multicast_ptr) + (lo * K + (k - 1)) * 4
+                        else:
+                            peer_recs = [int(hdls[k - 1].buffer_ptrs[q]) + lo * rb for q in others]
+                            peer_cards = [int(chdl.buffer_ptrs[q]) + (lo * K + (k - 1)) * 4 for q in others]
                         t0 = torch.cuda.Event(enable_timing=True)
                         t0.record()
                         ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
-                                       ws, peer_recs, peer_cards)
+                                       ws, peer_recs, peer_cards, mc_rec, mc_cards)
                         t1 = torch.cuda.Event(enable_timing=True)
                         t1.record()
                         self._merge_events.append((t0, t1))

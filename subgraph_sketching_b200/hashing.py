@@ -432,7 +432,7 @@ class ElphHashes(object):
 
     # ------------------------------------------------------------------ K2
     def _merge(self, rowptr, colidx, nnz, rec_in, rec_out, cards_col, device, ws=None, peer_recs=None,
-               peer_cards=None):
+               peer_cards=None, mc_rec=0, mc_cards=0):
         """one hop over the rows of `rec_out`; peer_recs / peer_cards: device addresses (ints) of the peers'
         copies of rec_out / cards_col for the fused multi-GPU exchange (ss_khop_merge_peers)"""
         d = self._consts(device)
@@ -442,14 +442,15 @@ class ElphHashes(object):
             ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
         ev = self._event_begin(device)
         n_peers = len(peer_recs) if peer_recs else 0
-        if n_peers:
-            pr = (ctypes.c_void_p * n_peers)(*peer_recs)
-            pc = (ctypes.c_void_p * n_peers)(*(peer_cards or [0] * n_peers))
+        if n_peers or mc_rec:
+            pr = (ctypes.c_void_p * max(n_peers, 1))(*(peer_recs or [0]))
+            pc = (ctypes.c_void_p * max(n_peers, 1))(*(peer_cards or [0] * max(n_peers, 1)))
             check(lib.ss_khop_merge_peers(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0],
                                           rec_in.stride(0), _ptr(rec_out), rec_out.stride(0), self.num_perm, self.p,
                                           _ptr(ws), ws.numel(), _ptr(cards_col),
                                           cards_col.stride(0) if cards_col is not None else 0, ctypes.byref(d['hc']),
                                           _lib.MERGE_VARIANTS[self.merge_variant], n_peers, pr, pc,
+                                          ctypes.c_void_p(mc_rec), ctypes.c_void_p(mc_cards),
                                           _stream_ptr(device)), 'ss_khop_merge_peers')
         else:
             check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0],

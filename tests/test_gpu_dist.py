@@ -63,6 +63,6 @@ def test_sharded_world1_matches_single_gpu():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-@pytest.mark.parametrize('exchange', ['nccl', 'auto'])
+@pytest.mark.parametrize('exchange', ['nccl', 'auto', 'mc'])
 def test_sharded_world2_matches_single_gpu(exchange):
     mp.spawn(_worker, args=(2, _free_port(), 13, 3, exchange), nprocs=2, join=True)
