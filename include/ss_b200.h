@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 5
+#define SS_ABI_VERSION 6
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -73,6 +73,7 @@ typedef struct ss_hll_consts {
 typedef struct ss_hop_view {
     const void *records;   /* device; compact records of all nodes for this hop */
     int64_t row_stride;    /* bytes between consecutive nodes */
+    int64_t num_rows;      /* nodes in the table (every link endpoint must be < num_rows) */
 } ss_hop_view;
 
 /* ---- library ------------------------------------------------------------------------------- */

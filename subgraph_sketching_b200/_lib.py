@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
 
-SS_ABI_VERSION = 5
+SS_ABI_VERSION = 6
 SS_FLAG_USE_ZERO_ONE = 1
 SS_FLAG_FLOOR = 2
 SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC, SS_MERGE_BULK = 0, 1, 2, 3, 4
@@ -31,7 +31,7 @@ class HllConsts(ctypes.Structure):
 
 class HopView(ctypes.Structure):
     """struct ss_hop_view"""
-    _fields_ = [('records', c_ptr), ('row_stride', c_i64)]
+    _fields_ = [('records', c_ptr), ('row_stride', c_i64), ('num_rows', c_i64)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/ss_b200.h

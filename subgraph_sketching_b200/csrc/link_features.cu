@@ -6,6 +6,9 @@
 // [n, m] float and [n, T] argsort temporaries; here one warp owns one link, loads the 2K records of (u, v)
 // once (each lane keeps 16 B of MinHash + 8 B of HLL per record in registers), evaluates all K^2
 // combinations from registers and finishes with the inclusion-exclusion algebra in the reference's order.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ss {
@@ -129,10 +132,89 @@ __device__ __forceinline__ uint32_t pow_sum_odd(uint32_t w) {
     return __funnelshift_r(0x10000000u, 0u, w >> 8) + __funnelshift_r(0x10000000u, 0u, w >> 24);
 }
 
+// all K^2 combinations, tails, algebra and stores of ONE link whose 2K records are in registers
 template <int K>
-__global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a) {
+__device__ __forceinline__ void process_link(const LinkArgs &a, int64_t i, const uint4 *mu, const uint2 *hu,
+                                             const uint4 *mv, const uint2 *hv, const float *cu, const float *cv,
+                                             int lane) {
     constexpr int F = K * (K + 2);
     constexpr int C = K * K;
+    RowRegs U[K], V[K];
+    uint32_t big = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        prep_row(U[k], mu[k], hu[k], big);
+        prep_row(V[k], mv[k], hv[k], big);
+    }
+    const bool any_big = __any_sync(FULL, big != 0u);  // rare: some register > 28 -> exact 128-bit path
+
+    // per-lane partial statistics of every combination c = (k1-1)*K + (k2-1)
+    uint32_t eq_pack[(C + 3) / 4] = {0};   // 8-bit fields: matches per lane <= 4, per warp <= 128
+    uint32_t nz_pack[(C + 2) / 3] = {0};   // 10-bit fields: non-zero registers per lane <= 8, per warp <= 256
+    int my_zeros = 0;
+    float my_S = 1.f;
+#pragma unroll
+    for (int k1 = 0; k1 < K; ++k1) {
+#pragma unroll
+        for (int k2 = 0; k2 < K; ++k2) {
+            const int c = k1 * K + k2;
+            const uint32_t eq = (U[k1].mh.x == V[k2].mh.x) + (U[k1].mh.y == V[k2].mh.y) +
+                                (U[k1].mh.z == V[k2].mh.z) + (U[k1].mh.w == V[k2].mh.w);
+            eq_pack[c / 4] += eq << (8 * (c % 4));
+            nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
+            const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
+            const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
+            float S;
+            if (!any_big) {
+                const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_odd(ox) + pow_sum_odd(oy);  // <= 2^31
+                const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
+                const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
+                const uint64_t total = (uint64_t)lo + ((uint64_t)hi << 16);
+                S = __fmul_rn(__ull2float_rn(total), 3.7252902984619140625e-09f);  // * 2^-28, exact
+            } else {
+                uint64_t acc = 0;
+                int nz = 0, zeros;
+                acc_regs_word(ex | ox, acc, nz);
+                acc_regs_word(ey | oy, acc, nz);
+                unsigned __int128 t = warp_total_units(acc, nz, zeros);
+                S = units_to_f32(t);
+                if (lane == c) my_zeros = zeros;
+            }
+            if (lane == c) my_S = S;
+        }
+    }
+    uint32_t my_match = 0;
+#pragma unroll
+    for (int w = 0; w < (C + 3) / 4; ++w) {
+        const uint32_t r = __reduce_add_sync(FULL, eq_pack[w]);
+        if (lane / 4 == w) my_match = (r >> (8 * (lane % 4))) & 0xffu;
+    }
+#pragma unroll
+    for (int w = 0; w < (C + 2) / 3; ++w) {
+        const uint32_t r = __reduce_add_sync(FULL, nz_pack[w]);
+        if (lane / 3 == w && !any_big) my_zeros = 256 - (int)((r >> (10 * (lane % 3))) & 0x3ffu);
+    }
+    float my_inter = 0.f;
+    if (lane < C) my_inter = intersection_tail(a.h, my_zeros, my_S, my_match, 128);
+    float I[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, c);
+    if (a.inter && lane < C) a.inter[i * C + lane] = my_inter;
+    if (a.features) {
+        float f[F];
+        feature_algebra<K>(I, cu, cv, f);
+        knockout_and_floor<K>(f, a.flags);
+        float mine = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; ++j)
+            if (lane == j) mine = f[j];
+        if (lane < F) a.features[i * F + lane] = mine;
+    }
+}
+
+// ---- LDG front end: the 2K records are loaded straight into registers -----------------------------------
+template <int K>
+__global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -155,77 +237,128 @@ __global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a)
             cu[k] = __ldg(a.cards + u * a.cards_stride + k);
             cv[k] = __ldg(a.cards + v * a.cards_stride + k);
         }
-        RowRegs U[K], V[K];
-        uint32_t big = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            prep_row(U[k], mu[k], hu[k], big);
-            prep_row(V[k], mv[k], hv[k], big);
-        }
-        const bool any_big = __any_sync(FULL, big != 0u);  // rare: some register > 28 -> exact 128-bit path
+        process_link<K>(a, i, mu, hu, mv, hv, cu, cv, lane);
+    }
+}
 
-        // per-lane partial statistics of every combination c = (k1-1)*K + (k2-1)
-        uint32_t eq_pack[(C + 3) / 4] = {0};   // 8-bit fields: matches per lane <= 4, per warp <= 128
-        uint32_t nz_pack[(C + 2) / 3] = {0};   // 10-bit fields: non-zero registers per lane <= 8, per warp <= 256
-        int my_zeros = 0;
-        float my_S = 1.f;
+// ---- TMA front end: links are processed in PAIRS; for each hop ONE gather4 (UTMALDG.2D.GATHER4) fetches
+// the four records (uA, vA, uB, vB) of the pair into the warp's shared-memory stage, two stages deep, so the
+// 12 records of the next pair are in flight while the current pair is being evaluated -- the load latency
+// that the LDG front end exposes (one link per warp at a time, no room for a register double buffer) is
+// hidden, and the 64-bit address arithmetic disappears (the TMA coordinates are the node ids).
+struct LinkMaps {
+    CUtensorMap m[3];
+};
+
+__device__ __forceinline__ void lk_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void lk_gather4(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int r0, int r1, int r2,
+                                           int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+__device__ __forceinline__ uint4 lk_lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint2 lk_lds_u2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+constexpr int LK_WARPS = 4;
+
+template <int K>
+__global__ void __launch_bounds__(LK_WARPS * 32) link_features_tma_kernel(const LinkArgs a,
+                                                                          const __grid_constant__ LinkMaps maps) {
+    constexpr uint32_t HOP_BYTES = 4 * 768;            // (uA, vA, uB, vB) of one hop
+    constexpr uint32_t STAGE = K * HOP_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t base = smem_u32(smem) + (uint32_t)warp * (2 * STAGE);
+    const uint32_t bars = smem_u32(smem) + (uint32_t)LK_WARPS * (2 * STAGE) + (uint32_t)warp * 16;
+    if (lane == 0) {
+        lk_mbar_init(bars, 1);
+        lk_mbar_init(bars + 8, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const int64_t n_pairs = (a.n_links + 1) >> 1;
+    const int64_t gwarp = (int64_t)blockIdx.x * LK_WARPS + warp;
+    const int64_t n_warps = (int64_t)gridDim.x * LK_WARPS;
+
+    // lanes 0..3 hold the node ids (uA, vA, uB, vB) of a pair; lanes < 4K its cards; lane 0 issues the TMA
+    auto fetch = [&](int64_t q, uint32_t stage, float &card) {
+        int64_t li = 2 * q + (lane >> 1);               // link of this lane's id (lanes 0,1 -> A; 2,3 -> B)
+        if (li >= a.n_links) li = a.n_links - 1;        // odd tail: B repeats A
+        int id = 0;
+        if (lane < 4) id = (int)__ldg(a.links + 2 * li + (lane & 1));
+        const int r0 = __shfl_sync(FULL, id, 0), r1 = __shfl_sync(FULL, id, 1);
+        const int r2 = __shfl_sync(FULL, id, 2), r3 = __shfl_sync(FULL, id, 3);
+        const int node = __shfl_sync(FULL, id, (lane / K) & 3);
+        card = (lane < 4 * K) ? __ldg(a.cards + (int64_t)node * a.cards_stride + (lane % K)) : 0.f;
+        if (lane == 0) {
+            const uint32_t bar = bars + 8 * stage;
+            lk_mbar_expect(bar, STAGE);
 #pragma unroll
-        for (int k1 = 0; k1 < K; ++k1) {
+            for (int k = 0; k < K; ++k) lk_gather4(base + stage * STAGE + k * HOP_BYTES, &maps.m[k], bar, r0, r1, r2, r3);
+        }
+    };
+
+    float card_next = 0.f;
+    uint32_t stage = 0, parity = 0;
+    if (gwarp < n_pairs) fetch(gwarp, 0, card_next);
+    for (int64_t q = gwarp; q < n_pairs; q += n_warps) {
+        const float card_cur = card_next;
+        if (q + n_warps < n_pairs) fetch(q + n_warps, stage ^ 1u, card_next);   // next pair into the other stage
+        lk_mbar_wait(bars + 8 * stage, parity);
+        const uint32_t rows = base + stage * STAGE;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int64_t i = 2 * q + half;
+            if (i >= a.n_links) break;
+            uint4 mu[K], mv[K];
+            uint2 hu[K], hv[K];
+            float cu[K], cv[K];
 #pragma unroll
-            for (int k2 = 0; k2 < K; ++k2) {
-                const int c = k1 * K + k2;
-                const uint32_t eq = (U[k1].mh.x == V[k2].mh.x) + (U[k1].mh.y == V[k2].mh.y) +
-                                    (U[k1].mh.z == V[k2].mh.z) + (U[k1].mh.w == V[k2].mh.w);
-                eq_pack[c / 4] += eq << (8 * (c % 4));
-                nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
-                const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
-                const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
-                float S;
-                if (!any_big) {
-                    const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_odd(ox) + pow_sum_odd(oy);  // <= 2^31
-                    const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
-                    const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
-                    const uint64_t total = (uint64_t)lo + ((uint64_t)hi << 16);
-                    S = __fmul_rn(__ull2float_rn(total), 3.7252902984619140625e-09f);  // * 2^-28, exact
-                } else {
-                    uint64_t acc = 0;
-                    int nz = 0, zeros;
-                    acc_regs_word(ex | ox, acc, nz);
-                    acc_regs_word(ey | oy, acc, nz);
-                    unsigned __int128 t = warp_total_units(acc, nz, zeros);
-                    S = units_to_f32(t);
-                    if (lane == c) my_zeros = zeros;
-                }
-                if (lane == c) my_S = S;
+            for (int k = 0; k < K; ++k) {
+                const uint32_t ru = rows + k * HOP_BYTES + (2 * half) * 768;
+                const uint32_t rv = ru + 768;
+                mu[k] = lk_lds_u4(ru + lane * 16);
+                hu[k] = lk_lds_u2(ru + REC_MH + lane * 8);
+                mv[k] = lk_lds_u4(rv + lane * 16);
+                hv[k] = lk_lds_u2(rv + REC_MH + lane * 8);
+                cu[k] = __shfl_sync(FULL, card_cur, (2 * half) * K + k);
+                cv[k] = __shfl_sync(FULL, card_cur, (2 * half + 1) * K + k);
             }
+            process_link<K>(a, i, mu, hu, mv, hv, cu, cv, lane);
         }
-        uint32_t my_match = 0;
-#pragma unroll
-        for (int w = 0; w < (C + 3) / 4; ++w) {
-            const uint32_t r = __reduce_add_sync(FULL, eq_pack[w]);
-            if (lane / 4 == w) my_match = (r >> (8 * (lane % 4))) & 0xffu;
-        }
-#pragma unroll
-        for (int w = 0; w < (C + 2) / 3; ++w) {
-            const uint32_t r = __reduce_add_sync(FULL, nz_pack[w]);
-            if (lane / 3 == w && !any_big) my_zeros = 256 - (int)((r >> (10 * (lane % 3))) & 0x3ffu);
-        }
-        float my_inter = 0.f;
-        if (lane < C) my_inter = intersection_tail(a.h, my_zeros, my_S, my_match, 128);
-        float I[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, c);
-        if (a.inter && lane < C) a.inter[i * C + lane] = my_inter;
-        if (a.features) {
-            float f[F];
-            feature_algebra<K>(I, cu, cv, f);
-            knockout_and_floor<K>(f, a.flags);
-            float mine = 0.f;
-#pragma unroll
-            for (int j = 0; j < F; ++j)
-                if (lane == j) mine = f[j];
-            if (lane < F) a.features[i * F + lane] = mine;
-        }
+        __syncwarp();  // all lanes are done with this stage before it is refilled two iterations later
+        if (stage == 1) parity ^= 1u;
+        stage ^= 1u;
     }
 }
 
@@ -288,12 +421,66 @@ __global__ void __launch_bounds__(256) link_features_generic_kernel(const LinkAr
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn lk_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// which front end.  Measured on B200 (R-MAT 24, K=3, 20 M links): LDG 27.8 ms, TMA pairs 37.2 ms -- the kernel is
+// instruction-bound (~900 warp instructions per link) and the TMA stages cap residency at 12 warps / SM, so
+// hiding the load latency does not pay for the lost issue slots.  LDG is the default; SS_B200_LINKS=tma opts in.
+static bool want_tma_links() {
+    const char *e = getenv("SS_B200_LINKS");
+    if (!(e && e[0] == 't')) return false;
+    return lk_encode_fn() != nullptr;
+}
+
 template <int K>
-static int launch_links(const LinkArgs &a, bool fast, cudaStream_t st) {
+static int launch_links(const LinkArgs &a, const int64_t *hop_rows, bool fast, cudaStream_t st) {
     int64_t blocks = (a.n_links + 7) / 8;
     int64_t cap = (int64_t)sm_count() * 16;
     int grid = (int)(blocks < cap ? blocks : cap);
-    if (fast) {
+    if (fast && want_tma_links()) {
+        LinkMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        for (int k = 0; k < 3; ++k) {
+            const int kk = k < K ? k + 1 : 1;  // unused maps repeat hop 1 (must still be valid descriptors)
+            cuuint64_t dims[2] = {192, (cuuint64_t)hop_rows[kk]};
+            cuuint64_t strides[1] = {(cuuint64_t)a.stride[kk]};
+            cuuint32_t box[2] = {192, 1};
+            cuuint32_t elem[2] = {1, 1};
+            CUresult r = lk_encode_fn()(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(a.hop[kk]), dims,
+                                        strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled failed with CUresult %d for hop %d", (int)r, kk);
+                return SS_ERR_CUDA;
+            }
+        }
+        const size_t smem = (size_t)LK_WARPS * 2 * K * 4 * 768 + LK_WARPS * 16;
+        auto k = link_features_tma_kernel<K>;
+        SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LK_WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        int64_t want = ((a.n_links + 1) / 2 + LK_WARPS - 1) / LK_WARPS;
+        int64_t resident = (int64_t)per_sm * sm_count();
+        k<<<(int)(want < resident ? want : resident), LK_WARPS * 32, smem, st>>>(a, maps);
+        SS_LAUNCH_CHECK("link_features_tma_kernel");
+    } else if (fast) {
         link_features_kernel<K><<<grid, 256, 0, st>>>(a);
         SS_LAUNCH_CHECK("link_features_kernel");
     } else {
@@ -322,6 +509,7 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
     if (rc != SS_OK) return rc;
     ss::LinkArgs a;
     memset(&a, 0, sizeof(a));
+    int64_t hop_rows[4] = {0, 0, 0, 0};
     a.links = links;
     a.n_links = n_links;
     for (int k = 1; k <= max_hops; ++k) {
@@ -329,6 +517,8 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
         SS_REQUIRE(hops[k].row_stride >= s.bytes && (hops[k].row_stride & 15) == 0, "hop %d has a bad row stride", k);
         a.hop[k] = (const uint8_t *)hops[k].records;
         a.stride[k] = hops[k].row_stride;
+        hop_rows[k] = hops[k].num_rows;
+        SS_REQUIRE(hops[k].num_rows > 0 && hops[k].num_rows < (1ll << 31), "hop %d: num_rows must be in (0, 2^31)", k);
     }
     // inter-only calls read no cards: point at a valid dummy (the hll lc table) with stride 0
     a.cards = cards ? cards : hc->lc_table;
@@ -341,9 +531,9 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
     const bool fast = (num_perm == 128 && hll_p == 8);
     cudaStream_t st = (cudaStream_t)stream;
     switch (max_hops) {
-        case 1: return ss::launch_links<1>(a, fast, st);
-        case 2: return ss::launch_links<2>(a, fast, st);
-        default: return ss::launch_links<3>(a, fast, st);
+        case 1: return ss::launch_links<1>(a, hop_rows, fast, st);
+        case 2: return ss::launch_links<2>(a, hop_rows, fast, st);
+        default: return ss::launch_links<3>(a, hop_rows, fast, st);
     }
 }
 

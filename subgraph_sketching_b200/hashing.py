@@ -533,6 +533,7 @@ class ElphHashes(object):
             keep.append(rec)
             views[k].records = rec.data_ptr()
             views[k].row_stride = rec.stride(0)
+            views[k].num_rows = rec.shape[0]
         return views, keep
 
     def _link_kernel(self, links, views, cards, device, want_features, want_inter):

@@ -422,3 +422,23 @@ def test_full_size_properties_rmat24():
             assert torch.equal(ia[(k1, k2)], ib[(k2, k1)])
     f = eh.get_subgraph_features(links, tables, cards)
     assert f.shape == (1_000_000, 15) and bool(torch.isfinite(f).all())
+
+
+def test_link_feature_front_ends_agree(monkeypatch):
+    """the TMA-pair front end (opt-in) must give the bits of the default LDG front end, odd link counts included"""
+    n = 1 << 13
+    ei = rmat_edges(13, 8, 5).to(DEV)
+    g = torch.Generator().manual_seed(2)
+    for K in (1, 2, 3):
+        eh = ssb.ElphHashes(make_args(K, use_zero_one=True))
+        tables, cards = eh.build_hash_tables(n, ei)
+        for L in (1, 2, 7, 4097):
+            links = torch.randint(0, n, (L, 2), generator=g).to(DEV)
+            monkeypatch.setenv('SS_B200_LINKS', 'ldg')
+            a = eh.get_subgraph_features(links, tables, cards)
+            ia = eh._get_intersections(links, tables)
+            monkeypatch.setenv('SS_B200_LINKS', 'tma')
+            b = eh.get_subgraph_features(links, tables, cards)
+            ib = eh._get_intersections(links, tables)
+            assert torch.equal(a, b), (K, L)
+            assert all(torch.equal(ia[k], ib[k]) for k in ia)
