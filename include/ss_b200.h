@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 6
+#define SS_ABI_VERSION 7
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -109,19 +109,24 @@ int ss_unpack_records(const void *rec, int64_t rec_stride, int64_t n, int num_pe
  * The reference scatters over the COO edge_index with self loops appended by
  * add_self_loops(edge_index) (hashing.py:148; PyG flow source -> target, aggregation at edge_index[1]).
  * Rows are destinations in [row_begin, row_begin + n_rows); a self loop (i, i) is added for every
- * i < n_self_loops that falls in the row range.  Two steps because nnz of a row shard is data dependent:
- *   ss_csr_rowptr : rowptr[0..n_rows] (int64, exclusive scan of in-degrees incl. self loops)
+ * i < n_self_loops that falls in the row range; n_self_loops < 0 means max(edge_index) + 1, computed on the
+ * device by ss_csr_rowptr -- exactly add_self_loops without num_nodes.  Two steps because nnz is data dependent:
+ *   ss_csr_rowptr : rowptr[0..n_rows] (int64, exclusive scan of in-degrees incl. self loops) and, when
+ *                   stats_out != NULL, stats_out[0..3] = { max id (-1 if no edges), nnz, self loops used, min id }
+ *                   (device int64[4]) plus optional int32 device copies src32_out / dst32_out of the endpoints
  *   ss_csr_fill   : colidx[0..nnz) (int32 global source ids), order inside a row is unspecified
- *                   (min/max merges are order independent)
+ *                   (min/max merges are order independent); reads the int32 copies when given
+ * src / dst are read with coalesced loads only, so they may be PINNED HOST pointers (UVA): the edge list is
+ * then consumed at PCIe rate with no staging copy, and with the int32 copies it crosses the bus once.
  * workspace: ss_csr_workspace_bytes(n_rows) bytes, 256-byte aligned, the same buffer for both calls.
  */
 int64_t ss_csr_workspace_bytes(int64_t n_rows);
 int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops,
-                  int64_t row_begin, int64_t n_rows, int64_t *rowptr, void *workspace, int64_t workspace_bytes,
-                  ss_stream_t stream);
-int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops,
-                int64_t row_begin, int64_t n_rows, const int64_t *rowptr, int32_t *colidx, void *workspace,
-                int64_t workspace_bytes, ss_stream_t stream);
+                  int64_t row_begin, int64_t n_rows, int64_t *rowptr, int32_t *src32_out, int32_t *dst32_out,
+                  int64_t *stats_out, void *workspace, int64_t workspace_bytes, ss_stream_t stream);
+int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,
+                int64_t n_self_loops, const int64_t *stats, int64_t row_begin, int64_t n_rows, const int64_t *rowptr,
+                int32_t *colidx, void *workspace, int64_t workspace_bytes, ss_stream_t stream);
 
 /* ---- K2: one hop of sketch propagation ----------------------------------------------------------
  * Replaces MinhashPropagation.forward + HllPropagation.forward (hashing.py:28-45, called at :160-162)
@@ -194,11 +199,14 @@ int ss_max_i8(const int8_t *a, const int8_t *b, int64_t count, int8_t *out, ss_s
  *   hops         HOST array of K+1 views indexed by hop (entry 0 is ignored)
  *   cards        float32, cards[node * cards_stride + (k-1)] = k-hop cardinality (hashing.py:163)
  *   features_out float32 [L, K(K+2)] or NULL;  inter_out float32 [L, K*K] (row-major (k1-1)*K+(k2-1)) or NULL
+ *   error_flag   device int32 or NULL: set to 1 when a link endpoint is outside [0, num_rows) (torch indexing in the
+ *                reference raises IndexError); such links are evaluated on node 0, never out of bounds.
+ *   links may be a PINNED HOST pointer (coalesced 16-byte reads over PCIe, 0.3 % of the kernel's traffic).
  */
 int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *hops, int max_hops,
                      int num_perm, int hll_p, const float *cards, int64_t cards_stride,
                      const ss_hll_consts *hc, int flags, float *features_out, float *inter_out,
-                     ss_stream_t stream);
+                     int32_t *error_flag, ss_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
 
-SS_ABI_VERSION = 6
+SS_ABI_VERSION = 7
 SS_FLAG_USE_ZERO_ONE = 1
 SS_FLAG_FLOOR = 2
 SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC, SS_MERGE_BULK = 0, 1, 2, 3, 4
@@ -44,8 +44,9 @@ SIGNATURES = {
     'ss_pack_records': (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr]),
     'ss_unpack_records': (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_csr_workspace_bytes': (c_i64, [c_i64]),
-    'ss_csr_rowptr': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
-    'ss_csr_fill': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_csr_rowptr': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_csr_fill': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
+                            c_ptr]),
     'ss_merge_workspace_bytes': (c_i64, [c_i64, c_int, c_int]),
     'ss_khop_merge': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64,
                               c_ptr, c_i64, ctypes.POINTER(HllConsts), c_int, c_ptr]),
@@ -59,7 +60,7 @@ SIGNATURES = {
     'ss_jaccard_i64': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
     'ss_max_i8': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     'ss_link_features': (c_int, [c_ptr, c_i64, ctypes.POINTER(HopView), c_int, c_int, c_int, c_ptr, c_i64,
-                                 ctypes.POINTER(HllConsts), c_int, c_ptr, c_ptr, c_ptr]),
+                                 ctypes.POINTER(HllConsts), c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
 

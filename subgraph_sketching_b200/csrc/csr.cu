@@ -36,12 +36,42 @@ static CsrWorkspace carve(void *ws, int64_t n_rows) {
     return w;
 }
 
-__global__ void __launch_bounds__(256) degree_kernel(const int64_t *__restrict__ dst, int64_t n_edges,
-                                                      int64_t row_begin, int64_t n_rows, uint32_t *deg) {
+// pass 1 over the COO list: in-degree histogram of the owned rows, max / min node id, and optional 32-bit device
+// copies of both endpoint arrays.  The loads are fully coalesced, so src / dst may live in pinned HOST memory and
+// are then consumed at PCIe rate with no staging copy (the 32-bit copies keep pass 2 off the bus).
+__global__ void __launch_bounds__(256) degree_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                                      int64_t n_edges, int64_t row_begin, int64_t n_rows, uint32_t *deg,
+                                                      int32_t *__restrict__ src32, int32_t *__restrict__ dst32,
+                                                      long long *stats) {
+    long long mx = -1, mn = 0x7fffffffffffffffll;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t d = dst[e] - row_begin;
+        const int64_t dv = dst[e];
+        const int64_t d = dv - row_begin;
         if (d >= 0 && d < n_rows) atomicAdd(deg + d, 1u);
+        if (stats) {
+            const int64_t sv = src[e];
+            mx = max(mx, (long long)max(sv, dv));
+            mn = min(mn, (long long)min(sv, dv));
+            if (src32) src32[e] = (int32_t)sv;
+            if (dst32) dst32[e] = (int32_t)dv;
+        }
     }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+            mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (mx >= 0) atomicMax(stats + 0, mx);
+            if (mn != 0x7fffffffffffffffll) atomicMin(stats + 3, mn);
+        }
+    }
+}
+
+// number of implicit self loops: given by the host, or max(edge_index) + 1 computed by pass 1
+__device__ __forceinline__ int64_t resolve_loops(int64_t n_self_loops, const long long *stats) {
+    return n_self_loops >= 0 ? n_self_loops : (int64_t)stats[0] + 1;
 }
 
 __device__ __forceinline__ int64_t row_degree(const uint32_t *deg, int64_t r, int64_t n_rows, int64_t row_begin,
@@ -64,9 +94,10 @@ __device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t *smem) {
 
 // phase 1: total of each tile of SCAN_TILE rows
 __global__ void __launch_bounds__(SCAN_BLOCK) tile_sum_kernel(const uint32_t *__restrict__ deg, int64_t n_rows,
-                                                               int64_t row_begin, int64_t n_self_loops,
-                                                               int64_t *__restrict__ tile_sum) {
+                                                               int64_t row_begin, int64_t n_self_loops_arg,
+                                                               const long long *stats, int64_t *__restrict__ tile_sum) {
     __shared__ int64_t sm[SCAN_BLOCK / 32];
+    const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int64_t v = 0;
 #pragma unroll
@@ -116,10 +147,11 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int64_t *tile_sum, int6
 
 // phase 3: exclusive scan inside each tile + tile offset -> rowptr
 __global__ void __launch_bounds__(SCAN_BLOCK) rowptr_kernel(const uint32_t *__restrict__ deg, int64_t n_rows,
-                                                             int64_t row_begin, int64_t n_self_loops,
-                                                             const int64_t *__restrict__ tile_off,
+                                                             int64_t row_begin, int64_t n_self_loops_arg,
+                                                             long long *stats, const int64_t *__restrict__ tile_off,
                                                              int64_t *__restrict__ rowptr) {
     __shared__ int64_t warp_tot[SCAN_BLOCK / 32];
+    const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int64_t d[SCAN_ITEMS];
@@ -145,19 +177,27 @@ __global__ void __launch_bounds__(SCAN_BLOCK) rowptr_kernel(const uint32_t *__re
         if (base + k < n_rows) rowptr[base + k] = run;
         run += d[k];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) rowptr[n_rows] = tile_off[gridDim.x];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        rowptr[n_rows] = tile_off[gridDim.x];
+        if (stats) {
+            stats[1] = tile_off[gridDim.x];  // nnz
+            stats[2] = n_self_loops;
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256) fill_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
-                                                    int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
-                                                    int64_t n_rows, const int64_t *__restrict__ rowptr,
+template <typename IdT>
+__global__ void __launch_bounds__(256) fill_kernel(const IdT *__restrict__ src, const IdT *__restrict__ dst,
+                                                    int64_t n_edges, int64_t n_self_loops_arg, const long long *stats,
+                                                    int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ rowptr,
                                                     uint32_t *cursor, int32_t *__restrict__ colidx) {
+    const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int64_t total = n_edges + n_rows;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t d, s;
         if (t < n_edges) {
-            d = dst[t] - row_begin;
-            s = src[t];
+            d = (int64_t)dst[t] - row_begin;
+            s = (int64_t)src[t];
             if (d < 0 || d >= n_rows) continue;
         } else {
             d = t - n_edges;
@@ -179,11 +219,14 @@ int64_t ss_csr_workspace_bytes(int64_t n_rows) {
 }
 
 int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
-                  int64_t n_rows, int64_t *rowptr, void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
-    (void)src;
-    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_self_loops >= 0 && row_begin >= 0, "negative size passed to ss_csr_rowptr");
+                  int64_t n_rows, int64_t *rowptr, int32_t *src32_out, int32_t *dst32_out, int64_t *stats_out,
+                  void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_rowptr");
     SS_REQUIRE(rowptr && workspace, "null pointer passed to ss_csr_rowptr");
     SS_REQUIRE(n_edges == 0 || dst, "dst is null");
+    SS_REQUIRE(n_self_loops >= 0 || stats_out, "n_self_loops < 0 (= max id + 1) needs stats_out");
+    SS_REQUIRE(!stats_out || n_edges == 0 || src, "src is required for the id statistics");
+    SS_REQUIRE(!(src32_out || dst32_out) || stats_out, "32-bit copies are written together with the statistics");
     SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     if (workspace_bytes < ss::workspace_bytes(n_rows)) {
         ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes,
@@ -191,33 +234,45 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
         return SS_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_rows == 0) {
+    long long *stats = (long long *)stats_out;
+    if (stats) {
+        const long long init[4] = {-1, 0, 0, 0x7fffffffffffffffll};
+        SS_CUDA(cudaMemcpyAsync(stats, init, sizeof(init), cudaMemcpyHostToDevice, st));  // staged before returning
+    }
+    if (n_rows == 0 && !stats) {
         SS_CUDA(cudaMemsetAsync(rowptr, 0, 8, st));
         return SS_OK;
     }
     ss::CsrWorkspace w = ss::carve(workspace, n_rows);
-    SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
+    if (n_rows > 0) SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
     if (n_edges > 0) {
         int64_t blocks = (n_edges + 255) / 256;
         int64_t cap = (int64_t)ss::sm_count() * 32;
-        ss::degree_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(dst, n_edges, row_begin, n_rows, w.deg);
+        ss::degree_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(src, dst, n_edges, row_begin, n_rows, w.deg,
+                                                                         src32_out, dst32_out, stats);
         SS_LAUNCH_CHECK("degree_kernel");
     }
-    ss::tile_sum_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, w.tile_sum);
+    if (n_rows == 0) {
+        SS_CUDA(cudaMemsetAsync(rowptr, 0, 8, st));
+        return SS_OK;
+    }
+    ss::tile_sum_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, stats, w.tile_sum);
     SS_LAUNCH_CHECK("tile_sum_kernel");
     ss::tile_scan_kernel<<<1, 1024, 0, st>>>(w.tile_sum, w.n_tiles);
     SS_LAUNCH_CHECK("tile_scan_kernel");
-    ss::rowptr_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, w.tile_sum, rowptr);
+    ss::rowptr_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, stats, w.tile_sum,
+                                                                rowptr);
     SS_LAUNCH_CHECK("rowptr_kernel");
     return SS_OK;
 }
 
-int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
-                int64_t n_rows, const int64_t *rowptr, int32_t *colidx, void *workspace, int64_t workspace_bytes,
-                ss_stream_t stream) {
-    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_self_loops >= 0 && row_begin >= 0, "negative size passed to ss_csr_fill");
+int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,
+                int64_t n_self_loops, const int64_t *stats, int64_t row_begin, int64_t n_rows, const int64_t *rowptr,
+                int32_t *colidx, void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_fill");
     SS_REQUIRE(rowptr && workspace, "null pointer passed to ss_csr_fill");
-    SS_REQUIRE(n_edges == 0 || (src && dst), "src/dst is null");
+    SS_REQUIRE(n_edges == 0 || (src && dst) || (src32 && dst32), "src/dst is null");
+    SS_REQUIRE(n_self_loops >= 0 || stats, "n_self_loops < 0 (= max id + 1) needs the statistics of ss_csr_rowptr");
     SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     if (workspace_bytes < ss::workspace_bytes(n_rows)) {
         ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes,
@@ -232,8 +287,14 @@ int ss_csr_fill(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t
     int64_t total = n_edges + n_rows;
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)ss::sm_count() * 32;
-    ss::fill_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(src, dst, n_edges, n_self_loops, row_begin, n_rows,
-                                                                       rowptr, w.deg, colidx);
+    int grid = (int)(blocks < cap ? blocks : cap);
+    if (src32 && dst32) {
+        ss::fill_kernel<int32_t><<<grid, 256, 0, st>>>(src32, dst32, n_edges, n_self_loops, (const long long *)stats, row_begin,
+                                                       n_rows, rowptr, w.deg, colidx);
+    } else {
+        ss::fill_kernel<int64_t><<<grid, 256, 0, st>>>(src, dst, n_edges, n_self_loops, (const long long *)stats, row_begin,
+                                                       n_rows, rowptr, w.deg, colidx);
+    }
     SS_LAUNCH_CHECK("fill_kernel");
     return SS_OK;
 }

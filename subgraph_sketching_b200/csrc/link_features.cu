@@ -27,7 +27,16 @@ struct LinkArgs {
     float *features;
     float *inter;
     RecordShape s;
+    int64_t n_nodes;  // rows of the smallest hop table: link endpoints must be in [0, n_nodes)
+    int *err;         // set to 1 if any endpoint is out of range (such links are evaluated on node 0)
 };
+
+// bounds check of a link endpoint (the reference would raise IndexError from torch indexing)
+__device__ __forceinline__ int64_t checked_node(const LinkArgs &a, int64_t id) {
+    if ((uint64_t)id < (uint64_t)a.n_nodes) return id;
+    if (a.err) atomicExch(a.err, 1);
+    return 0;
+}
 
 // scalar tail: (zeros, S = sum 2^-r as float, matches) -> jaccard * union cardinality (hashing.py:184-187)
 __device__ __forceinline__ float intersection_tail(const HllDev &h, int zeros, float S, uint32_t matches, int P) {
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a)
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = gwarp; i < a.n_links; i += n_warps) {
-        const int64_t u = __ldg(a.links + 2 * i), v = __ldg(a.links + 2 * i + 1);
+        const int64_t u = checked_node(a, __ldg(a.links + 2 * i)), v = checked_node(a, __ldg(a.links + 2 * i + 1));
         uint4 mu[K], mv[K];
         uint2 hu[K], hv[K];
 #pragma unroll
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) link_features_tma_kernel(const 
         int64_t li = 2 * q + (lane >> 1);               // link of this lane's id (lanes 0,1 -> A; 2,3 -> B)
         if (li >= a.n_links) li = a.n_links - 1;        // odd tail: B repeats A
         int id = 0;
-        if (lane < 4) id = (int)__ldg(a.links + 2 * li + (lane & 1));
+        if (lane < 4) id = (int)checked_node(a, __ldg(a.links + 2 * li + (lane & 1)));
         const int r0 = __shfl_sync(FULL, id, 0), r1 = __shfl_sync(FULL, id, 1);
         const int r2 = __shfl_sync(FULL, id, 2), r3 = __shfl_sync(FULL, id, 3);
         const int node = __shfl_sync(FULL, id, (lane / K) & 3);
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(256) link_features_generic_kernel(const LinkAr
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = gwarp; i < a.n_links; i += n_warps) {
-        const int64_t u = __ldg(a.links + 2 * i), v = __ldg(a.links + 2 * i + 1);
+        const int64_t u = checked_node(a, __ldg(a.links + 2 * i)), v = checked_node(a, __ldg(a.links + 2 * i + 1));
         float cu[K], cv[K], I[K * K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -496,7 +505,7 @@ extern "C" {
 
 int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *hops, int max_hops, int num_perm,
                      int hll_p, const float *cards, int64_t cards_stride, const ss_hll_consts *hc, int flags,
-                     float *features_out, float *inter_out, ss_stream_t stream) {
+                     float *features_out, float *inter_out, int32_t *error_flag, ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(max_hops >= 1 && max_hops <= 3, "Only 1, 2 and 3 hop hashes are implemented (got %d)", max_hops);
@@ -528,6 +537,10 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
     a.features = features_out;
     a.inter = inter_out;
     a.s = s;
+    a.err = error_flag;
+    a.n_nodes = hop_rows[1];
+    for (int k = 2; k <= max_hops; ++k)
+        if (hop_rows[k] < a.n_nodes) a.n_nodes = hop_rows[k];
     const bool fast = (num_perm == 128 && hll_p == 8);
     cudaStream_t st = (cudaStream_t)stream;
     switch (max_hops) {

@@ -31,7 +31,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .hashing import ElphHashes, HopSketch, SketchTables, _ptr, _stream_ptr, _to_device, check, lib
+from .hashing import ElphHashes, HopSketch, SketchTables, _edge_source, _ptr, _stream_ptr, check, lib
 
 
 def shard_bounds(num_nodes, world_size, rank):
@@ -151,20 +151,24 @@ class ShardedElphHashes(object):
 
     def _local_csr(self, edge_index, num_nodes, device):
         """global rowptr (every rank computes the same one) -> balanced bounds -> this rank's CSR rows"""
-        ei = _to_device(edge_index, device)
-        ei = (ei if ei.dtype == torch.int64 else ei.long()).contiguous()
+        ei, zero_copy = _edge_source(edge_index, device)
         n_edges = ei.shape[1]
-        max_id = int(ei.max()) if n_edges else -1
-        if max_id >= num_nodes:
-            raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
-        n_loops = max_id + 1
         src, dst = ei[0], ei[1]
         ws_bytes = check(lib.ss_csr_workspace_bytes(num_nodes), 'ss_csr_workspace_bytes')
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
         rowptr_g = torch.empty(num_nodes + 1, dtype=torch.int64, device=device)
+        stats = torch.empty(4, dtype=torch.int64, device=device)
+        src32 = dst32 = None
+        if zero_copy and n_edges:  # host-resident edge list: keep 32-bit device copies for the fill pass
+            src32 = torch.empty(n_edges, dtype=torch.int32, device=device)
+            dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
         st = _stream_ptr(device)
-        check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, n_loops, 0, num_nodes, _ptr(rowptr_g), _ptr(ws),
-                                ws.numel(), st), 'ss_csr_rowptr')
+        check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, -1, 0, num_nodes, _ptr(rowptr_g), _ptr(src32),
+                                _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
+        max_id, _, n_loops, min_id = (int(v) for v in stats.tolist())
+        if max_id >= num_nodes or (n_edges and min_id < 0):
+            raise IndexError(f'edge_index refers to node {max_id if max_id >= num_nodes else min_id} but num_nodes '
+                             f'is {num_nodes}')
         bounds = balanced_bounds(rowptr_g, self.world_size, default_row_weight(self.world_size, self.exchange),
                                  self.shares)
         lo, hi = bounds[self.rank], bounds[self.rank + 1]
@@ -172,8 +176,8 @@ class ShardedElphHashes(object):
         nnz = int(rowptr[-1]) if hi > lo else 0
         colidx = torch.empty(max(nnz, 4), dtype=torch.int32, device=device)
         if hi > lo:
-            check(lib.ss_csr_fill(_ptr(src), _ptr(dst), n_edges, n_loops, lo, hi - lo, _ptr(rowptr), _ptr(colidx),
-                                  _ptr(ws), ws.numel(), st), 'ss_csr_fill')
+            check(lib.ss_csr_fill(_ptr(src), _ptr(dst), _ptr(src32), _ptr(dst32), n_edges, n_loops, None, lo, hi - lo,
+                                  _ptr(rowptr), _ptr(colidx), _ptr(ws), ws.numel(), st), 'ss_csr_fill')
         return rowptr, colidx, nnz, bounds
 
     def _update_shares(self, device):

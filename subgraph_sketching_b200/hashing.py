@@ -150,7 +150,7 @@ class _CsrCache(object):
                                                                         device=ei.device)).sum()))
 
     def get(self, edge_index, device, add_loops):
-        ei = _to_device(edge_index, device)
+        ei = edge_index.to(device, non_blocking=True) if edge_index.device != device else edge_index
         ei = (ei if ei.dtype == torch.int64 else ei.long()).contiguous()
         key = (tuple(ei.shape), str(device), add_loops, self.fingerprint(ei))
         if key != self.key:
@@ -159,30 +159,51 @@ class _CsrCache(object):
         return self.value
 
 
-def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0):
-    """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [nnz], nnz) keyed by destination
-    (PyG flow source -> target, hashing.py:30-35).  With add_loops, a self loop is appended for every node id
-    < max(edge_index)+1, which is add_self_loops(edge_index) without num_nodes (hashing.py:148)."""
-    ei = _to_device(edge_index, device)
+def _edge_source(edge_index, device):
+    """(tensor whose storage the CSR kernels read, zero_copy flag).  A pinned host edge_index is NOT copied:
+    the kernels read it in place over PCIe with coalesced loads (UVA), so the list crosses the bus once and
+    never occupies device memory; pageable host tensors and other dtypes are copied to the device."""
+    ei = edge_index
+    if ei.dim() != 2 or ei.shape[0] != 2:
+        raise ValueError('edge_index must be [2, n_edges]')
+    if ei.device.type == 'cpu' and ei.dtype == torch.int64 and ei.is_contiguous() and ei.is_pinned():
+        return ei, True
+    ei = ei.to(device, non_blocking=True) if ei.device != device else ei
     if ei.dtype != torch.int64:
         ei = ei.long()
-    ei = ei.contiguous()
+    return ei.contiguous(), False
+
+
+def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bounds_fn=None):
+    """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [nnz], nnz, max_id) keyed by destination
+    (PyG flow source -> target, hashing.py:30-35).  With add_loops, a self loop is appended for every node id
+    < max(edge_index)+1 (computed on the device), which is add_self_loops(edge_index) without num_nodes
+    (hashing.py:148).  One device->host read (32 bytes of statistics) sizes colidx."""
+    ei, zero_copy = _edge_source(edge_index, device)
     n_edges = ei.shape[1]
-    max_id = int(ei.max()) if n_edges else -1
-    n_loops = (max_id + 1) if add_loops else 0
-    if num_rows is None:
-        num_rows = max_id + 1
+    if num_rows is None:  # rows = max id + 1: needs the id statistics first
+        num_rows = (int(ei.max()) + 1) if n_edges else 0
     src, dst = ei[0], ei[1]
     ws_bytes = check(lib.ss_csr_workspace_bytes(num_rows), 'ss_csr_workspace_bytes')
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
     rowptr = torch.empty(num_rows + 1, dtype=torch.int64, device=device)
+    stats = torch.empty(4, dtype=torch.int64, device=device)
+    src32 = dst32 = None
+    if zero_copy and n_edges:
+        src32 = torch.empty(n_edges, dtype=torch.int32, device=device)
+        dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
     st = _stream_ptr(device)
-    check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, n_loops, row_begin, num_rows, _ptr(rowptr), _ptr(ws),
-                            ws.numel(), st), 'ss_csr_rowptr')
-    nnz = int(rowptr[-1])
-    colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)
-    check(lib.ss_csr_fill(_ptr(src), _ptr(dst), n_edges, n_loops, row_begin, num_rows, _ptr(rowptr), _ptr(colidx),
-                          _ptr(ws), ws.numel(), st), 'ss_csr_fill')
+    loops = -1 if add_loops else 0
+    check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, loops, row_begin, num_rows, _ptr(rowptr), _ptr(src32),
+                            _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
+    max_id, nnz, _, min_id = (int(v) for v in stats.tolist())
+    if n_edges and min_id < 0:
+        raise IndexError(f'edge_index holds a negative node id ({min_id})')
+    if max_id >= (1 << 31):
+        raise IndexError('node ids must be < 2^31')
+    colidx = torch.empty(max(nnz, 4), dtype=torch.int32, device=device)
+    check(lib.ss_csr_fill(_ptr(src), _ptr(dst), _ptr(src32), _ptr(dst32), n_edges, loops, _ptr(stats), row_begin,
+                          num_rows, _ptr(rowptr), _ptr(colidx), _ptr(ws), ws.numel(), st), 'ss_csr_fill')
     return rowptr, colidx, nnz, max_id
 
 
@@ -508,7 +529,11 @@ class ElphHashes(object):
             logger.info(f'hash generation enqueued in {time() - start} s')
             tables = SketchTables({k: HopSketch(recs[k], self.num_perm, self.p, out_device)
                                    for k in range(self.max_hops + 1)}, self.num_perm, self.p)
-            return tables, (cards if out_device == device else _to_host(cards))
+            if out_device == device:
+                return tables, cards
+            cards_host = _to_host(cards)
+            cards_host._ss_device_copy = (cards, cards_host._version)  # spares get_subgraph_features the re-upload
+            return tables, cards_host
 
     # ------------------------------------------------------------------ K4
     def _hop_views(self, hash_table, device):
@@ -536,32 +561,26 @@ class ElphHashes(object):
             views[k].num_rows = rec.shape[0]
         return views, keep
 
-    def _link_kernel(self, links, views, cards, device, want_features, want_inter):
-        d = self._consts(device)
-        n = links.shape[0]
-        K = self.max_hops
-        feats = torch.empty((n, K * (K + 2)), dtype=torch.float32, device=device) if want_features else None
-        inter = torch.empty((n, K * K), dtype=torch.float32, device=device) if want_inter else None
-        flags = (_lib.SS_FLAG_USE_ZERO_ONE if self.use_zero_one else 0) | (_lib.SS_FLAG_FLOOR if self.floor_sf else 0)
-        check(lib.ss_link_features(_ptr(links), n, views, K, self.num_perm, self.p, _ptr(cards),
-                                   cards.stride(0) if cards is not None else 0, ctypes.byref(d['hc']), flags,
-                                   _ptr(feats), _ptr(inter), _stream_ptr(device)), 'ss_link_features')
-        return feats, inter
+    def _flags(self):
+        return (_lib.SS_FLAG_USE_ZERO_ONE if self.use_zero_one else 0) | (_lib.SS_FLAG_FLOOR if self.floor_sf else 0)
 
-    def _check_links(self, links, hash_table, device):
+    def _link_source(self, links, device):
+        """links as the kernel reads them: device int64 [n, 2], or the caller's PINNED host tensor in place
+        (16 bytes per link read over PCIe, 0.3 % of the kernel's traffic -- no staging copy)"""
         if self.max_hops not in (1, 2, 3):
             raise NotImplementedError("Only 1, 2 and 3 hop hashes are implemented")
-        ld = _to_device(links, device)
-        ld = (ld if ld.dtype == torch.int64 else ld.long()).contiguous()
-        if ld.dim() != 2 or ld.shape[1] != 2:
+        if links.dim() != 2 or links.shape[1] != 2:
             raise ValueError('links must be [n_edges, 2]')
-        if self.validate_links and ld.numel():
-            entry = dict.__getitem__(hash_table, 1) if isinstance(hash_table, SketchTables) else hash_table[1]
-            n_nodes = entry.records.shape[0] if isinstance(entry, HopSketch) else entry['hll'].shape[0]
-            lo, hi = int(ld.min()), int(ld.max())
-            if lo < 0 or hi >= n_nodes:
-                raise IndexError(f'link endpoint out of range [0, {n_nodes}): min {lo}, max {hi}')
-        return ld
+        if links.device.type == 'cpu' and links.dtype == torch.int64 and links.is_contiguous() and links.is_pinned():
+            return links
+        ld = links.to(device, non_blocking=True) if links.device != device else links
+        return (ld if ld.dtype == torch.int64 else ld.long()).contiguous()
+
+    def _raise_if_flagged(self, err, views):
+        """the kernels never read out of bounds; with validate_links the flag they set becomes the reference's
+        IndexError (costs one 4-byte device->host read, i.e. a stream synchronisation)"""
+        if self.validate_links and int(err.item()):
+            raise IndexError(f'link endpoint out of range [0, {int(views[1].num_rows)})')
 
     def _get_intersections(self, edge_list, hash_table):
         """
@@ -570,12 +589,19 @@ class ElphHashes(object):
         @return: {(k1, k2): float32 [n_edges]} for k1, k2 in 1..max_hops
         """
         device = _cuda_device(edge_list)
+        K = self.max_hops
         with torch.cuda.device(device):
-            ld = self._check_links(edge_list, hash_table, device)
+            d = self._consts(device)
+            ld = self._link_source(edge_list, device)
             views, keep = self._hop_views(hash_table, device)
-            _, inter = self._link_kernel(ld, views, None, device, False, True)
-            inter = inter.to(edge_list.device)
-            K = self.max_hops
+            n = ld.shape[0]
+            inter = torch.empty((n, K * K), dtype=torch.float32, device=device)
+            err = torch.zeros(1, dtype=torch.int32, device=device)
+            check(lib.ss_link_features(_ptr(ld), n, views, K, self.num_perm, self.p, None, 0, ctypes.byref(d['hc']),
+                                       self._flags(), None, _ptr(inter), _ptr(err), _stream_ptr(device)),
+                  'ss_link_features')
+            self._raise_if_flagged(err, views)
+            inter = inter if edge_list.device == device else _to_host(inter)
             return {(k1, k2): inter[:, (k1 - 1) * K + (k2 - 1)] for k1 in range(1, K + 1) for k2 in range(1, K + 1)}
 
     def get_subgraph_features(self, links, hash_table, cards, batch_size=11000000):
@@ -592,27 +618,72 @@ class ElphHashes(object):
             links = links.unsqueeze(0)
         device = _cuda_device(links)
         K = self.max_hops
+        F = K * (K + 2)
         with torch.cuda.device(device):
             views, keep = self._hop_views(hash_table, device)
-            cd = _to_device(cards, device)
-            cd = (cd if cd.dtype == torch.float32 else cd.float()).contiguous()
+            cached = getattr(cards, '_ss_device_copy', None)  # device twin of a cards tensor we returned to the host
+            if cached is not None and cached[1] == cards._version and cached[0].device == device:
+                cd = cached[0]
+            else:
+                cd = cards.to(device, non_blocking=True) if cards.device != device else cards
+                cd = (cd if cd.dtype == torch.float32 else cd.float()).contiguous()
             if cd.dim() != 2 or cd.shape[1] < K:
                 raise ValueError('cards must be [n_nodes, max_hops]')
-            ld = self._check_links(links, hash_table, device)
+            ld = self._link_source(links, device)
             n = ld.shape[0]
-            out = torch.empty((n, K * (K + 2)), dtype=torch.float32, device=device)
-            batch_size = max(int(batch_size), 1)
             d = self._consts(device)
-            flags = (_lib.SS_FLAG_USE_ZERO_ONE if self.use_zero_one else 0) | \
-                    (_lib.SS_FLAG_FLOOR if self.floor_sf else 0)
-            for lo in range(0, n, batch_size):
-                hi = min(lo + batch_size, n)
+            flags = self._flags()
+            err = torch.zeros(1, dtype=torch.int32, device=device)
+            batch_size = max(int(batch_size), 1)
+            main = torch.cuda.current_stream(device)
+
+            def launch(lo, hi, out_rows):
                 ev = self._event_begin(device)
                 check(lib.ss_link_features(_ptr(ld[lo:hi]), hi - lo, views, K, self.num_perm, self.p, _ptr(cd),
-                                           cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out[lo:hi]), None,
+                                           cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out_rows), None, _ptr(err),
                                            _stream_ptr(device)), 'ss_link_features')
                 self._event_end('link_features', ev, device)
-            return out if links.device == device else _to_host(out)
+
+            if links.device == device:
+                out = torch.empty((n, F), dtype=torch.float32, device=device)
+                for lo in range(0, n, batch_size):
+                    hi = min(lo + batch_size, n)
+                    launch(lo, hi, out[lo:hi])
+                self._raise_if_flagged(err, views)
+                return out
+            # host result: kernels on the current stream, device->pinned-host copies of finished batches on a
+            # side stream, double buffered -- the copy of batch b overlaps the kernel of batch b + 1
+            try:
+                out = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
+            except RuntimeError:
+                out = torch.empty((n, F), dtype=torch.float32)
+            step = max(min(batch_size, 1 << 21), 1)
+            side = self._side_stream(device)
+            bufs = [torch.empty((min(step, max(n, 1)), F), dtype=torch.float32, device=device) for _ in range(2)]
+            freed = [None, None]
+            for b, lo in enumerate(range(0, n, step)):
+                hi = min(lo + step, n)
+                buf = bufs[b & 1][:hi - lo]
+                if freed[b & 1] is not None:
+                    main.wait_event(freed[b & 1])
+                launch(lo, hi, buf)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    out[lo:hi].copy_(buf, non_blocking=True)
+                    freed[b & 1] = torch.cuda.Event()
+                    freed[b & 1].record(side)
+            side.synchronize()
+            main.synchronize()
+            self._raise_if_flagged(err, views)
+            return out
+
+    def _side_stream(self, device):
+        key = 'side:' + str(device)
+        if key not in self._dev:
+            self._dev[key] = torch.cuda.Stream(device=device)
+        return self._dev[key]
 
     # ------------------------------------------------------------------ K3 / K5 helpers
     def get_hashval(self, x):

@@ -442,3 +442,35 @@ def test_link_feature_front_ends_agree(monkeypatch):
             ib = eh._get_intersections(links, tables)
             assert torch.equal(a, b), (K, L)
             assert all(torch.equal(ia[k], ib[k]) for k in ia)
+
+
+def test_pinned_host_inputs_are_read_in_place():
+    """BUDDY-style CPU inputs: a pinned edge_index / link list is consumed by the kernels over PCIe without a
+    staging copy; results equal the device-resident path bit for bit, out-of-range ids still raise"""
+    n, K = 6000, 2
+    g = torch.Generator().manual_seed(31)
+    ei = torch.randint(0, n - 10, (2, 50000), generator=g)
+    links = torch.randint(0, n, (70001, 2), generator=g)
+    eh = ssb.ElphHashes(make_args(K))
+    t_dev, c_dev = eh.build_hash_tables(n, ei.to(DEV))
+    f_dev = eh.get_subgraph_features(links.to(DEV), t_dev, c_dev)
+    for pin in (True, False):
+        e_h = ei.pin_memory() if pin else ei
+        l_h = links.pin_memory() if pin else links
+        t_h, c_h = eh.build_hash_tables(n, e_h)
+        assert not c_h.is_cuda and torch.equal(c_h, c_dev.cpu())
+        for k in range(K + 1):
+            assert torch.equal(t_h.records(k), t_dev.records(k))
+        f_h = eh.get_subgraph_features(l_h, t_h, c_h, batch_size=20000)
+        assert not f_h.is_cuda and torch.equal(f_h, f_dev.cpu())
+        c_h[0, 0] += 1.0  # a modified cards tensor must not be served from its stale device twin
+        f_mod = eh.get_subgraph_features(l_h[:16], t_h, c_h)
+        c_ref = c_dev.clone()
+        c_ref[0, 0] += 1.0
+        assert torch.equal(f_mod, eh.get_subgraph_features(links[:16].to(DEV), t_dev, c_ref).cpu())
+    bad = links.clone()
+    bad[5, 1] = n
+    with pytest.raises(IndexError):
+        eh.get_subgraph_features(bad.pin_memory(), t_dev, c_dev)
+    with pytest.raises(IndexError):
+        eh.build_hash_tables(n, torch.tensor([[0, -1], [1, 2]]).pin_memory())
