@@ -43,8 +43,8 @@ def parse():
     ap.add_argument('--hops', type=int, default=None)
     ap.add_argument('--links', type=int, default=None, help='candidate links per step')
     ap.add_argument('--merge-variant', default='auto', choices=['auto', 'tma', 'ldg', 'generic'])
-    ap.add_argument('--cpu-scale', type=int, default=16, help='R-MAT scale of the bounded CPU-baseline sample')
-    ap.add_argument('--ref-scale', type=int, default=15, help='R-MAT scale of each --impl reference step')
+    ap.add_argument('--cpu-scale', type=int, default=17, help='R-MAT scale of the bounded CPU-baseline sample')
+    ap.add_argument('--ref-scale', type=int, default=17, help='R-MAT scale of each --impl reference step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'mc', 'nccl'], help='multi-GPU exchange mode')
@@ -340,7 +340,12 @@ def main():
 
         e2e_step()
         e2e_steps = max(1, min(a.steps, 3))
+        eh.event_log = []
         e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
+        e2e_log, eh.event_log = eh.event_log, None
+        e2e_stage = {}
+        for name, s_, e_ in e2e_log:
+            e2e_stage[name] = e2e_stage.get(name, 0.0) + s_.elapsed_time(e_) / e2e_steps
         if distributed:
             h2d = ei_h.numel() * 8 + L_local * 16
             d2h = L_local * F * 4
@@ -348,7 +353,7 @@ def main():
             h2d = ei_h.numel() * 8 + links_h.numel() * 8  # read in place by the kernels; cards keep a device twin
             d2h = N * K * 4 + L * F * 4
         e2e = {'value': L / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-               'ms_per_step': e2e_ms, 'steps': e2e_steps}
+               'ms_per_step': e2e_ms, 'steps': e2e_steps, 'stage_ms_per_step': e2e_stage}
         del ei_h, links_h
 
     # ---- bounded CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
