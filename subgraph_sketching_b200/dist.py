@@ -194,7 +194,7 @@ class ShardedElphHashes(object):
         # throughput of rank r = share_r / t_r; next shares proportional to it (damped)
         speed = [o / x for o, x in zip(old, t)]
         tot = sum(speed)
-        new = [0.5 * o + 0.5 * (v / tot) for o, v in zip(old, speed)]
+        new = [0.3 * o + 0.7 * (v / tot) for o, v in zip(old, speed)]
         tot = sum(new)
         self.shares = [v / tot for v in new]
 
