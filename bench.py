@@ -43,7 +43,7 @@ def parse():
     ap.add_argument('--hops', type=int, default=None)
     ap.add_argument('--links', type=int, default=None, help='candidate links per step')
     ap.add_argument('--merge-variant', default='auto', choices=['auto', 'tma', 'ldg', 'generic'])
-    ap.add_argument('--cpu-scale', type=int, default=17, help='R-MAT scale of the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-scale', type=int, default=18, help='R-MAT scale of the bounded CPU-baseline sample')
     ap.add_argument('--ref-scale', type=int, default=17, help='R-MAT scale of each --impl reference step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
