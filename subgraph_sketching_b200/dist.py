@@ -163,9 +163,24 @@ class ShardedElphHashes(object):
             src32 = torch.empty(n_edges, dtype=torch.int32, device=device)
             dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
         st = _stream_ptr(device)
-        check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, -1, 0, num_nodes, _ptr(rowptr_g), _ptr(src32),
-                                _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
-        max_id, _, n_loops, min_id = (int(v) for v in stats.tolist())
+        G, r = self.world_size, self.rank
+        if G > 1 and not zero_copy and n_edges >= (1 << 10):
+            # sharded histogram pass: rank r scans only its 1/G slice of the edge list; prefix sums are linear,
+            # so the global rowptr is the SUM over ranks of the partial ones (one all-reduce) plus the self loops
+            e_lo, e_hi = (n_edges * r) // G, (n_edges * (r + 1)) // G
+            check(lib.ss_csr_rowptr(_ptr(src[e_lo:e_hi]), _ptr(dst[e_lo:e_hi]), e_hi - e_lo, 0, 0, num_nodes,
+                                    _ptr(rowptr_g), None, None, _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
+            dist.all_reduce(rowptr_g, op=dist.ReduceOp.SUM, group=self.group)
+            ext = torch.stack([stats[0], -stats[3]])
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=self.group)
+            max_id, min_id = int(ext[0]), -int(ext[1])
+            n_loops = max_id + 1
+            if 0 <= max_id < num_nodes:  # self loop of node i < n_loops adds 1 to every prefix entry above i
+                rowptr_g += torch.arange(num_nodes + 1, device=device, dtype=torch.int64).clamp_(max=n_loops)
+        else:
+            check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, -1, 0, num_nodes, _ptr(rowptr_g), _ptr(src32),
+                                    _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
+            max_id, _, n_loops, min_id = (int(v) for v in stats.tolist())
         if max_id >= num_nodes or (n_edges and min_id < 0):
             raise IndexError(f'edge_index refers to node {max_id if max_id >= num_nodes else min_id} but num_nodes '
                              f'is {num_nodes}')
