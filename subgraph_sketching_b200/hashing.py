@@ -210,8 +210,9 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
 class MinhashPropagation(object):
     """element-wise min over in-neighbours (hashing.py:28-35).  `edge_index` already holds the self loops."""
 
-    def __init__(self, csr_cache=None):
-        self._csr = csr_cache if csr_cache is not None else _CsrCache()
+    def __init__(self, owner=None):
+        self.owner = owner
+        self._csr = owner._csr_cache if owner is not None else _CsrCache()
 
     @torch.no_grad()
     def __call__(self, x, edge_index):
@@ -219,14 +220,15 @@ class MinhashPropagation(object):
 
     @torch.no_grad()
     def forward(self, x, edge_index):
-        return _propagate(x, edge_index, self._csr, is_min=True)
+        return _propagate(x, edge_index, self._csr, True, self.owner)
 
 
 class HllPropagation(object):
     """register-wise max over in-neighbours (hashing.py:38-45)"""
 
-    def __init__(self, csr_cache=None):
-        self._csr = csr_cache if csr_cache is not None else _CsrCache()
+    def __init__(self, owner=None):
+        self.owner = owner
+        self._csr = owner._csr_cache if owner is not None else _CsrCache()
 
     @torch.no_grad()
     def __call__(self, x, edge_index):
@@ -234,28 +236,40 @@ class HllPropagation(object):
 
     @torch.no_grad()
     def forward(self, x, edge_index):
-        return _propagate(x, edge_index, self._csr, is_min=False)
+        return _propagate(x, edge_index, self._csr, False, self.owner)
 
 
-def _propagate(x, edge_index, cache, is_min):
+def _propagate(x, edge_index, cache, is_min, owner=None):
+    """operator form on the reference's tensors (ELPH calls it 2K times per forward, models/elph.py:209-212).
+    Sketch-shaped inputs (int64 [N,128] MinHash values in [0, 2^32) / int8 [N,256] registers >= 0) on graphs
+    that are worth it go through the record engine: pack -> hub-balanced TMA merge -> unpack.  Anything else
+    (other widths, other value ranges, tiny graphs) takes the plain row-per-warp kernel."""
     device = _cuda_device(x)
     want = torch.int64 if is_min else torch.int8
-    xd = _to_device(x, device)
-    if xd.dtype != want:
-        xd = xd.to(want)
-    xd = xd.contiguous()
-    n, width = xd.shape
-    rowptr, colidx, nnz, max_id = cache.get(edge_index, device, False)
-    if max_id >= n:
-        raise IndexError(f'edge_index refers to node {max_id} but x has {n} rows')
-    if rowptr.numel() - 1 < n:  # nodes above max(edge_index): no in-edges -> zero rows
-        pad = rowptr[-1:].expand(n - (rowptr.numel() - 1))
-        rowptr = torch.cat([rowptr, pad])
-    out = torch.empty_like(xd)
-    fn = lib.ss_prop_min_i64 if is_min else lib.ss_prop_max_i8
-    check(fn(_ptr(rowptr), _ptr(colidx), n, _ptr(xd), _ptr(out), width, _stream_ptr(device)), 'ss_prop')
-    out = out.to(x.dtype) if out.dtype != x.dtype else out
-    return out if x.device == device else out.to(x.device)
+    with torch.cuda.device(device):
+        xd = _to_device(x, device)
+        if xd.dtype != want:
+            xd = xd.to(want)
+        xd = xd.contiguous()
+        n, width = xd.shape
+        rowptr, colidx, nnz, max_id = cache.get(edge_index, device, False)
+        if max_id >= n:
+            raise IndexError(f'edge_index refers to node {max_id} but x has {n} rows')
+        if rowptr.numel() - 1 < n:  # nodes above max(edge_index): no in-edges -> zero rows
+            pad = rowptr[-1:].expand(n - (rowptr.numel() - 1))
+            rowptr = torch.cat([rowptr, pad])
+        out = None
+        if (owner is not None and owner.num_perm == 128 and owner.p == 8 and width == (128 if is_min else 256)
+                and nnz >= owner.fast_prop_min_nnz):
+            lo, hi = (int(v) for v in torch.aminmax(xd))
+            if lo >= 0 and hi < ((1 << 32) if is_min else 128):
+                out = owner._propagate_records(xd, rowptr, colidx, nnz, is_min, device)
+        if out is None:
+            out = torch.empty_like(xd)
+            fn = lib.ss_prop_min_i64 if is_min else lib.ss_prop_max_i8
+            check(fn(_ptr(rowptr), _ptr(colidx), n, _ptr(xd), _ptr(out), width, _stream_ptr(device)), 'ss_prop')
+        out = out.to(x.dtype) if out.dtype != x.dtype else out
+        return out if x.device == device else out.to(x.device)
 
 
 class HopSketch(object):
@@ -342,7 +356,8 @@ class ElphHashes(object):
         self.minhash_seed = 1
         self.num_perm = args.minhash_num_perm
         self._csr_cache = _CsrCache()  # shared by both operators
-        self.minhash_prop = MinhashPropagation(self._csr_cache)
+        self.fast_prop_min_nnz = 1 << 16  # operator forms use the record engine from this many neighbours up
+        self.minhash_prop = MinhashPropagation(self)
         # hll params (hashing.py:64-81)
         self.p = args.hll_p
         self.m = 1 << self.p
@@ -360,7 +375,7 @@ class ElphHashes(object):
         self.hll_threshold = threshold
         self.bias_vector = torch.tensor(np.asarray(bias, dtype=np.float64), dtype=torch.float)
         self.estimate_vector = torch.tensor(np.asarray(raw_estimate, dtype=np.float64), dtype=torch.float)
-        self.hll_prop = HllPropagation(self._csr_cache)
+        self.hll_prop = HllPropagation(self)
         self.merge_variant = merge_variant
         self.validate_links = True  # bounds-check link endpoints (the reference raises IndexError)
         self.event_log = None  # set to a list to record (name, start_event, end_event) around kernels
@@ -495,6 +510,28 @@ class ElphHashes(object):
         end = torch.cuda.Event(enable_timing=True)
         end.record(torch.cuda.current_stream(device))
         self.event_log.append((name, start, end))
+
+    def _propagate_records(self, xd, rowptr, colidx, nnz, is_min, device):
+        """one operator-form hop through the record engine; the unused half of the records is never read back"""
+        n = xd.shape[0]
+        rb = self._record_bytes()
+        rec_in = torch.empty((n, rb), dtype=torch.uint8, device=device)
+        rec_out = torch.empty((n, rb), dtype=torch.uint8, device=device)
+        st = _stream_ptr(device)
+        if is_min:
+            rec_in[:, 4 * self.num_perm:].zero_()  # keep the (ignored) register half defined
+            check(lib.ss_pack_records(_ptr(xd), None, n, self.num_perm, self.p, _ptr(rec_in), rec_in.stride(0), st),
+                  'ss_pack_records')
+        else:
+            rec_in[:, :4 * self.num_perm].zero_()
+            check(lib.ss_pack_records(None, _ptr(xd), n, self.num_perm, self.p, _ptr(rec_in), rec_in.stride(0), st),
+                  'ss_pack_records')
+        self._merge(rowptr, colidx, nnz, rec_in, rec_out, None, device)
+        out = torch.empty_like(xd)
+        check(lib.ss_unpack_records(_ptr(rec_out), rec_out.stride(0), n, self.num_perm, self.p,
+                                    _ptr(out) if is_min else None, None if is_min else _ptr(out), st),
+              'ss_unpack_records')
+        return out
 
     def build_hash_tables(self, num_nodes, edge_index):
         """

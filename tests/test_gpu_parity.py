@@ -474,3 +474,27 @@ def test_pinned_host_inputs_are_read_in_place():
         eh.get_subgraph_features(bad.pin_memory(), t_dev, c_dev)
     with pytest.raises(IndexError):
         eh.build_hash_tables(n, torch.tensor([[0, -1], [1, 2]]).pin_memory())
+
+
+def test_operator_forms_use_record_engine_on_large_graphs():
+    """hll_prop / minhash_prop on a hub-heavy graph: the record-engine route (pack -> TMA merge -> unpack) and the
+    plain row-per-warp kernels must agree with the oracle and with each other; out-of-range values fall back"""
+    scale = 13
+    n = 1 << scale
+    ei = so.with_self_loops(rmat_edges(scale, 16, 11))
+    eh = ssb.ElphHashes(make_args(2))
+    mh0, hl0 = eh.initialise_minhash(n), eh.initialise_hll(n)
+    want_m, want_h = so.minhash_propagate(mh0, ei), so.hll_propagate(hl0, ei)
+    ei_d, mh_d, hl_d = ei.to(DEV), mh0.to(DEV), hl0.to(DEV)
+    assert ei.shape[1] >= eh.fast_prop_min_nnz
+    fast_m, fast_h = eh.minhash_prop(mh_d, ei_d), eh.hll_prop(hl_d, ei_d)
+    eh.fast_prop_min_nnz = 1 << 62
+    slow_m, slow_h = eh.minhash_prop(mh_d, ei_d), eh.hll_prop(hl_d, ei_d)
+    eh.fast_prop_min_nnz = 1 << 16
+    assert torch.equal(fast_m.cpu(), want_m) and torch.equal(slow_m, fast_m)
+    assert torch.equal(fast_h.cpu(), want_h) and torch.equal(slow_h, fast_h)
+    # values outside the sketch range (negative / >= 2^32) keep the exact int64 semantics of the reference
+    weird = mh_d.clone()
+    weird[5, 7] = -3
+    weird[9, 1] = 1 << 40
+    assert torch.equal(eh.minhash_prop(weird, ei_d).cpu(), so.minhash_propagate(weird.cpu(), ei))
