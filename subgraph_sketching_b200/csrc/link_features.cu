@@ -171,25 +171,48 @@ __device__ __forceinline__ void process_link(const LinkArgs &a, int64_t i, const
                                 (U[k1].mh.z == V[k2].mh.z) + (U[k1].mh.w == V[k2].mh.w);
             eq_pack[c / 4] += eq << (8 * (c % 4));
             nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
-            const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
-            const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
-            float S;
-            if (!any_big) {
+        }
+    }
+    // the (rare) exact path is hoisted out of the combination loop so that the common path is straight-line
+    // code: the K^2 independent reduction chains (REDUX -> I2F -> FMUL) can then overlap instead of each one
+    // waiting behind a branch
+    if (!any_big) {
+#pragma unroll
+        for (int k1 = 0; k1 < K; ++k1) {
+#pragma unroll
+            for (int k2 = 0; k2 < K; ++k2) {
+                const int c = k1 * K + k2;
+                const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
+                const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
                 const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_odd(ox) + pow_sum_odd(oy);  // <= 2^31
                 const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
                 const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
-                const uint64_t total = (uint64_t)lo + ((uint64_t)hi << 16);
-                S = __fmul_rn(__ull2float_rn(total), 3.7252902984619140625e-09f);  // * 2^-28, exact
-            } else {
-                uint64_t acc = 0;
-                int nz = 0, zeros;
-                acc_regs_word(ex | ox, acc, nz);
-                acc_regs_word(ey | oy, acc, nz);
-                unsigned __int128 t = warp_total_units(acc, nz, zeros);
-                S = units_to_f32(t);
-                if (lane == c) my_zeros = zeros;
+                // lo < 2^21 and hi < 2^20 are exact in float32 and so is hi * 2^16: one rounding in the add gives
+                // the correctly rounded total
+                const float S = __fmul_rn(__fadd_rn(__fmul_rn((float)hi, 65536.f), (float)lo), 3.7252902984619140625e-09f);
+                if (lane == c) my_S = S;
             }
-            if (lane == c) my_S = S;
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            const int k1 = c / K, k2 = c % K;
+            uint2 ue = make_uint2(0u, 0u), uo = ue, ve = ue, vo = ue;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {  // select without dynamic register indexing
+                if (k == k1) { ue = U[k].he; uo = U[k].ho; }
+                if (k == k2) { ve = V[k].he; vo = V[k].ho; }
+            }
+            uint64_t acc = 0;
+            int nz = 0, zeros;
+            acc_regs_word(__vmaxu2(ue.x, ve.x) | __vmaxu2(uo.x, vo.x), acc, nz);
+            acc_regs_word(__vmaxu2(ue.y, ve.y) | __vmaxu2(uo.y, vo.y), acc, nz);
+            unsigned __int128 t = warp_total_units(acc, nz, zeros);
+            const float S = units_to_f32(t);
+            if (lane == c) {
+                my_S = S;
+                my_zeros = zeros;
+            }
         }
     }
     uint32_t my_match = 0;

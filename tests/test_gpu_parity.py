@@ -498,3 +498,32 @@ def test_operator_forms_use_record_engine_on_large_graphs():
     weird[5, 7] = -3
     weird[9, 1] = 1 << 40
     assert torch.equal(eh.minhash_prop(weird, ei_d).cpu(), so.minhash_propagate(weird.cpu(), ei))
+
+
+def test_link_features_exact_path_for_large_registers():
+    """registers above 28 leave the 32-bit fixed-point fast path: arbitrary (synthetic) tables in the reference
+    layout, registers up to 57, against the oracle -- for both link-feature front ends"""
+    n = 500
+    g = torch.Generator().manual_seed(77)
+    for K in (1, 2, 3):
+        tables = {}
+        for k in range(K + 1):
+            hll = torch.randint(0, 58, (n, 256), generator=g).to(torch.int8)
+            hll[torch.rand((n, 256), generator=g) < 0.3] = 0
+            hll[:50] = torch.clamp(hll[:50], max=20)          # some rows stay on the fast path
+            tables[k] = {'hll': hll, 'minhash': torch.randint(0, 6, (n, 128), generator=g)}
+        cards = torch.rand((n, K), generator=g) * 1000
+        links = torch.randint(0, n, (3001, 2), generator=g)
+        links[:500] = torch.randint(0, 50, (500, 2), generator=g)
+        o = so.OracleSketches(K, 128, 8, use_zero_one=True, floor_sf=False)
+        want = o.intersections(links, tables)
+        wf = o.subgraph_features(links, tables, cards)
+        eh = ssb.ElphHashes(make_args(K, use_zero_one=True))
+        got = eh._get_intersections(links.to(DEV), tables)
+        for key in want:
+            ok, err = float_close(got[key].cpu(), want[key], want[key].abs())
+            assert ok, (K, key, err)
+        gf = eh.get_subgraph_features(links.to(DEV), tables, cards)
+        scale = torch.maximum(link_scale(links, cards), torch.stack([v.abs() for v in want.values()]).max(dim=0).values)
+        ok, err = float_close(gf.cpu(), wf, scale)
+        assert ok, (K, err)
