@@ -527,3 +527,30 @@ def test_link_features_exact_path_for_large_registers():
         scale = torch.maximum(link_scale(links, cards), torch.stack([v.abs() for v in want.values()]).max(dim=0).values)
         ok, err = float_close(gf.cpu(), wf, scale)
         assert ok, (K, err)
+
+
+def test_cache_round_trip_in_reference_formats(tmp_path):
+    """features / hashes / cards are cached under the reference's names and formats; a second
+    call is served from the caches (first from the hash cache, then from the feature cache) with the same bits"""
+    from subgraph_sketching_b200 import cache
+    blob = load_golden('ba300_k3')
+    ei = torch.from_numpy(blob['edge_index'])
+    links = torch.from_numpy(blob['links'])
+    root = str(tmp_path) + '/'
+    eh = engine_for(blob, use_zero_one=False, floor_sf=True)
+    f1 = cache.preprocess_subgraph_features(eh, root, 'train', links, ei, 300, num_negs=1, load_hashes=True)
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == ['train_3hop_cardcache.pt', 'train_3hop_hashcache.pt']
+    hashes = torch.load(root + 'train_3hop_hashcache.pt')            # the reference's plain mapping of CPU tensors
+    assert sorted(hashes.keys()) == [0, 1, 2, 3] and hashes[2]['minhash'].dtype == torch.int64
+    assert np.array_equal(hashes[3]['hll'].numpy(), blob['hll_3'])
+    assert np.array_equal(torch.load(root + 'train_3hop_cardcache.pt').numpy(), eh.build_hash_tables(300, ei)[1].numpy())
+    f2 = cache.preprocess_subgraph_features(eh, root, 'train', links, ei, 300, load_hashes=True,
+                                            cache_subgraph_features=True)     # from the hash cache
+    assert torch.equal(f1, f2)
+    assert (tmp_path / 'train_3hop_subgraph_featurecache.pt').exists()
+    f3 = cache.preprocess_subgraph_features(eh, root, 'train', links, None, 300, cache_subgraph_features=True)
+    assert torch.equal(f1, f3)                                                 # from the feature cache
+    ok, err = float_close(f1, blob['features_zo0_fl1'], link_scale(blob['links'], blob['cards']))
+    assert ok, err
+    assert cache.generate_file_names(root, 'train', 2, 5)[0].endswith('train_negs5_subgraph_featurecache.pt')

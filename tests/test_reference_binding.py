@@ -81,3 +81,26 @@ def test_reference_models_bind_b200_engine():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_cache_file_names_match_reference():
+    """subgraph_sketching_b200.cache reproduces HashDataset._generate_file_names (datasets/elph.py:154-173)"""
+    import types
+    from subgraph_sketching_b200 import cache
+    _stub_pyg_for_models()
+    tg_data = types.ModuleType('torch_geometric.data')
+    tg_data.Dataset = object
+    sys.modules.setdefault('torch_geometric.data', tg_data)
+    import torch_sparse
+    torch_sparse.coalesce = getattr(torch_sparse, 'coalesce', None)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = importlib.import_module('src.datasets.elph')
+    for hops in (1, 2, 3):
+        for split in ('train', 'valid', 'test'):
+            for negs in (1, 5):
+                for ds, year in (('Cora', 0), ('ogbl-collab', 2010), ('ogbl-collab', 0)):
+                    fake = types.SimpleNamespace(max_hash_hops=hops, split=split, root='/tmp/x/',
+                                                 args=types.SimpleNamespace(dataset_name=ds, year=year))
+                    want = ref.HashDataset._generate_file_names(fake, negs)
+                    assert cache.generate_file_names('/tmp/x/', split, hops, negs, ds, year) == want
