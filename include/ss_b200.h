@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 7
+#define SS_ABI_VERSION 8
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -207,6 +207,19 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
                      int num_perm, int hll_p, const float *cards, int64_t cards_stride,
                      const ss_hll_consts *hc, int flags, float *features_out, float *inter_out,
                      int32_t *error_flag, ss_stream_t stream);
+
+/* ---- next row: common-neighbour heuristics on a SORTED CSR adjacency ------------
+ * Replaces CN / AA / RA of /root/reference/src/heuristics.py:11-71 (scipy A[src].multiply(A_[dst]) row sums;
+ * HashDataset computes RA with it when --use_RA, datasets/elph.py:76-77):
+ *     out[i] = float32( sum over w in N(u) & N(v) of  A[u,w] * (A[v,w] * mult[w]) ),  (u, v) = links[i]
+ * rowptr int64 [n_nodes+1], colidx int32 sorted and unique inside each row, weights float64 [nnz] or NULL (= 1),
+ * mult float64 [n_nodes] (1 for CN, 1/log(colsum) for AA, 1/colsum for RA; infinities replaced by 0 as the
+ * reference does).  ss_col_sums gives colsum (= A.sum(axis=0), also the `degrees` of datasets/elph.py:74).
+ */
+int ss_col_sums(const int32_t *colidx, const double *weights, int64_t nnz, int64_t n_cols, double *out, ss_stream_t stream);
+int ss_common_neighbour_scores(const int64_t *rowptr, const int32_t *colidx, const double *weights, const double *mult,
+                               int64_t n_nodes, const int64_t *links, int64_t n_links, float *out, int32_t *error_flag,
+                               ss_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -121,5 +121,51 @@ def main():
     print('hll_count_p8 written')
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and 'heuristics' not in sys.argv:
     main()
+
+
+class _NumpyLinks(object):
+    """[n, 2] link list with the two torch-tensor methods heuristics.py uses (`.size(0)`, `[ind, col]`), answering
+    with numpy arrays: the scipy in this image (1.18) rejects torch tensors as sparse-matrix indices, which the
+    reference's `A[src]` would otherwise hand it.  The reference functions themselves run unmodified."""
+
+    def __init__(self, arr):
+        self.arr = np.asarray(arr)
+
+    def size(self, dim):
+        return self.arr.shape[dim]
+
+    def __getitem__(self, key):
+        ind, col = key
+        return self.arr[np.asarray(ind), col]
+
+
+def heuristics_golden():
+    """CN / AA / RA of the unmodified reference on a weighted multigraph and a BA graph"""
+    import importlib
+    ref_loader.load()
+    heur = importlib.import_module('src.heuristics')
+    import scipy.sparse as ssp
+    blob = {}
+    g = torch.Generator().manual_seed(5)
+    cases = {'ba300': (300, barabasi_albert(300, 8, 1), None),
+             'multi': (150, torch.randint(0, 150, (2, 1500), generator=g), torch.randint(1, 4, (1500,), generator=g))}
+    for name, (n, ei, w) in cases.items():
+        wv = np.ones(ei.shape[1]) if w is None else w.numpy().astype(float)
+        A = ssp.csr_matrix((wv, (ei[0].numpy(), ei[1].numpy())), shape=(n, n))
+        links = torch.randint(0, n, (500, 2), generator=g)
+        links[:100] = ei[:, :100].t()
+        blob[f'{name}_n'] = n
+        blob[f'{name}_edge_index'] = ei.numpy()
+        blob[f'{name}_weight'] = wv
+        blob[f'{name}_links'] = links.numpy()
+        for kind, fn in (('cn', heur.CN), ('aa', heur.AA), ('ra', heur.RA)):
+            blob[f'{name}_{kind}'] = fn(A, _NumpyLinks(links.numpy()))[0].numpy()
+        blob[f'{name}_degrees'] = np.asarray(A.sum(axis=0, dtype=float)).flatten()
+    np.savez_compressed(os.path.join(OUT_DIR, 'heuristics.npz'), **blob)
+    print('heuristics written')
+
+
+if __name__ == '__main__' and 'heuristics' in sys.argv:
+    heuristics_golden()

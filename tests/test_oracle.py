@@ -119,3 +119,14 @@ def test_oracle_matches_live_reference(K, P, p, seed):
         assert torch.equal(ot[k]['hll'], rt[k]['hll'])
     assert torch.equal(oc, rc)
     assert torch.equal(o.subgraph_features(links, ot, oc), rf)
+
+
+def test_heuristics_oracle_matches_reference_golden():
+    """CN / AA / RA restatement (oracle/heuristics_oracle.py) vs the unmodified reference (heuristics.py:11-71)"""
+    from oracle import heuristics_oracle as ho
+    blob = load_golden('heuristics')
+    for name in ('ba300', 'multi'):
+        A = ho.adjacency(blob[f'{name}_edge_index'], int(blob[f'{name}_n']), blob[f'{name}_weight'])
+        for kind in ('cn', 'aa', 'ra'):
+            got = ho.scores(A, blob[f'{name}_links'], kind)
+            assert np.array_equal(got.numpy(), blob[f'{name}_{kind}']), (name, kind)
