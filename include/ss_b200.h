@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 9
+#define SS_ABI_VERSION 8
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -93,12 +93,10 @@ int64_t ss_record_bytes(int num_perm, int hll_p);
  *                numpy so the device reproduces the reference's bit_length quirk exactly.
  * Returns SS_ERR_INVALID semantics of hashing.py:101-103 are impossible here: rank >= 1 always holds for
  * 64-bit hashes, so no overflow error exists.
- * hop0_hll_out (optional, hll_p == 8 only): uint16 [n], (register index << 8 | rank) of the single non-zero HLL
- *                register of each hop-0 row -- the side table of the hop-1 shortcut of ss_khop_merge_peers.
  */
 int ss_init_records(int64_t n, int64_t first_id, int num_perm, int hll_p, const uint64_t *perm_a,
                     const uint64_t *perm_b, const int32_t *log2_window, void *rec_out, int64_t out_stride,
-                    uint16_t *hop0_hll_out, ss_stream_t stream);
+                    ss_stream_t stream);
 
 /* reference layout (int64 [n,P] MinHash, int8 [n,m] HLL)  <->  compact records; either side of the
  * pair may be NULL to skip it.  These back `hash_table[k]['minhash']` / `['hll']` (hashing.py:153-154). */
@@ -159,18 +157,13 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
  * mc_rec_out / mc_cards_out (optional, else NULL): NVSwitch MULTICAST addresses of the same buffers
  * (cuMulticast / symmetric memory `multicast_ptr`), addressed like rec_out / cards_out; when given, every
  * store is ONE `multimem.st` that the switch replicates into all GPUs' copies (the writer's included) and the
- * peer arrays are ignored.  P=128 / p=8 engines only.
- * hop0_hll (optional, else NULL; TMA / bulk engines): rec_in is the HOP-0 table and hop0_hll its side table from
- * ss_init_records, indexed like rec_in.  A hop-0 HLL row has one non-zero register, so only the 512-byte MinHash
- * half of every neighbour record is gathered and the register comes from the 2-byte (L2-resident) side table:
- * a third less DRAM traffic for the first hop, identical results. */
+ * peer arrays are ignored.  P=128 / p=8 engines only. */
 #define SS_MAX_PEERS 7
 int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
                         int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p,
                         void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
                         const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
-                        float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, const uint16_t *hop0_hll,
-                        ss_stream_t stream);
+                        float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, ss_stream_t stream);
 
 /* operator forms on the reference's own tensor layouts (ELPH calls these per batch,
  * /root/reference/src/models/elph.py:209-212): element-wise signed min (int64) / max (int8) over

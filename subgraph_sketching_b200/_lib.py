@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
 
-SS_ABI_VERSION = 9
+SS_ABI_VERSION = 8
 SS_FLAG_USE_ZERO_ONE = 1
 SS_FLAG_FLOOR = 2
 SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC, SS_MERGE_BULK = 0, 1, 2, 3, 4
@@ -40,7 +40,7 @@ SIGNATURES = {
     'ss_last_error': (ctypes.c_char_p, []),
     'ss_device_info': (c_int, [ctypes.POINTER(c_int)] * 3),
     'ss_record_bytes': (c_i64, [c_int, c_int]),
-    'ss_init_records': (c_int, [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    'ss_init_records': (c_int, [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_pack_records': (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr]),
     'ss_unpack_records': (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_csr_workspace_bytes': (c_i64, [c_i64]),
@@ -52,7 +52,7 @@ SIGNATURES = {
                               c_ptr, c_i64, ctypes.POINTER(HllConsts), c_int, c_ptr]),
     'ss_khop_merge_peers': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr,
                                     c_i64, c_ptr, c_i64, ctypes.POINTER(HllConsts), c_int, c_int,
-                                    ctypes.POINTER(c_ptr), ctypes.POINTER(c_ptr), c_ptr, c_ptr, c_ptr, c_ptr]),
+                                    ctypes.POINTER(c_ptr), ctypes.POINTER(c_ptr), c_ptr, c_ptr, c_ptr]),
     'ss_prop_min_i64': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_prop_max_i8': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_hll_count': (c_int, [c_ptr, c_i64, c_i64, ctypes.POINTER(HllConsts), c_ptr, c_i64, c_ptr]),

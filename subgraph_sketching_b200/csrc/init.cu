@@ -43,8 +43,7 @@ __global__ void __launch_bounds__(256) init_records_kernel(int64_t n, uint64_t f
                                                             const uint64_t *__restrict__ pa,
                                                             const uint64_t *__restrict__ pb,
                                                             const int32_t *__restrict__ window,
-                                                            uint8_t *__restrict__ out, int64_t out_stride,
-                                                            uint16_t *__restrict__ hop0_hll) {
+                                                            uint8_t *__restrict__ out, int64_t out_stride) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -53,7 +52,6 @@ __global__ void __launch_bounds__(256) init_records_kernel(int64_t n, uint64_t f
         const uint32_t slot = (uint32_t)(h & (uint64_t)(s.m - 1));
         const int rank = (64 - s.p) - ref_bit_length(h >> s.p, window) + 1;
         uint8_t *row = out + i * out_stride;
-        if (hop0_hll && lane == 0) hop0_hll[i] = (uint16_t)((slot << 8) | (uint32_t)rank);
         for (int u = lane; u < s.units; u += 32) {
             uint2 v;
             if (u < s.mh_units) {
@@ -127,7 +125,7 @@ extern "C" {
 
 int ss_init_records(int64_t n, int64_t first_id, int num_perm, int hll_p, const uint64_t *perm_a,
                     const uint64_t *perm_b, const int32_t *log2_window, void *rec_out, int64_t out_stride,
-                    uint16_t *hop0_hll_out, ss_stream_t stream) {
+                    ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n >= 0, "n must be >= 0");
@@ -137,8 +135,7 @@ int ss_init_records(int64_t n, int64_t first_id, int num_perm, int hll_p, const 
     SS_REQUIRE(out_stride >= s.bytes && (out_stride & 15) == 0, "bad record stride %lld", (long long)out_stride);
     int grid = ss::grid_for(n * 32, 256);
     ss::init_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, (uint64_t)first_id, s, perm_a, perm_b,
-                                                                   log2_window, (uint8_t *)rec_out, out_stride,
-                                                                   hll_p == 8 ? hop0_hll_out : nullptr);
+                                                                   log2_window, (uint8_t *)rec_out, out_stride);
     SS_LAUNCH_CHECK("init_records_kernel");
     return SS_OK;
 }

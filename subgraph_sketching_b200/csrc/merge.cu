@@ -53,10 +53,6 @@ struct MergeArgs {
     int n_peers;
     uint8_t *peer_out[SS_MAX_PEERS];
     float *peer_cards[SS_MAX_PEERS];
-    // hop-1 shortcut: hop-0 HLL rows hold ONE non-zero register, kept as (slot << 8 | rank) per node in a 2-byte side
-    // table (33 MB at 16.8 M nodes, L2 resident); when given, only the 512-byte MinHash half of the hop-0 records is
-    // gathered (a third less DRAM traffic for this hop)
-    const uint16_t *hop0_hll;
     // NVSwitch multicast alternative: ONE multimem.st per store lands in every GPU's copy (own copy included)
     uint8_t *mc_out;
     float *mc_cards;
@@ -167,29 +163,6 @@ __device__ __forceinline__ void acc_merge(RowState &st, const uint4 &m, const ui
     st.he.y = __vmaxu2(st.he.y, h.y & EVEN);
     st.ho.x = __vmaxu2(st.ho.x, h.x & ODD);
     st.ho.y = __vmaxu2(st.ho.y, h.y & ODD);
-}
-// MinHash part only (hop-1 shortcut) and the single hop-0 register of a neighbour given as (slot << 8 | rank)
-__device__ __forceinline__ void acc_merge_mh(RowState &st, const uint4 &m) {
-    st.mh.x = min(st.mh.x, m.x);
-    st.mh.y = min(st.mh.y, m.y);
-    st.mh.z = min(st.mh.z, m.z);
-    st.mh.w = min(st.mh.w, m.w);
-}
-__device__ __forceinline__ void acc_merge_mh2(RowState &st, const uint4 &m1, const uint4 &m2) {
-    st.mh.x = __vimin3_u32(st.mh.x, m1.x, m2.x);
-    st.mh.y = __vimin3_u32(st.mh.y, m1.y, m2.y);
-    st.mh.z = __vimin3_u32(st.mh.z, m1.z, m2.z);
-    st.mh.w = __vimin3_u32(st.mh.w, m1.w, m2.w);
-}
-__device__ __forceinline__ void acc_merge_reg(RowState &st, uint32_t slot_rank, int lane) {
-    const uint32_t slot = slot_rank >> 8, rank = slot_rank & 0xffu;
-    const uint32_t b = slot & 7u;                                   // byte inside this lane's 8 registers
-    const uint32_t v = ((int)(slot >> 3) == lane) ? rank << (8u * (b & 3u)) : 0u;
-    const uint32_t lo = (b < 4u) ? v : 0u, hi = (b < 4u) ? 0u : v;
-    st.he.x = __vmaxu2(st.he.x, lo & EVEN);
-    st.ho.x = __vmaxu2(st.ho.x, lo & ODD);
-    st.he.y = __vmaxu2(st.he.y, hi & EVEN);
-    st.ho.y = __vmaxu2(st.ho.y, hi & ODD);
 }
 // two neighbour rows at once: three-input min / max (VIMNMX3)
 __device__ __forceinline__ void acc_merge2(RowState &st, const uint4 &m1, const uint2 &h1, const uint4 &m2,
@@ -340,12 +313,11 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     return r;
 }
 
-template <int S, int WARPS, int MIN_CTAS, bool GATHER4, bool HOP1>
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const MergeArgs a,
                                                                            const __grid_constant__ CUtensorMap tmap) {
     constexpr int G = 4;
-    constexpr uint32_t ROWB = HOP1 ? REC_MH : REC;   // bytes of a neighbour row that are staged
-    constexpr uint32_t STAGE = G * ROWB;
+    constexpr uint32_t STAGE = G * REC;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -396,10 +368,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
                 if (GATHER4) {
                     tma_gather4(dst, &tmap, bar, 0, ids.x, ids.y, ids.z, ids.w);
                 } else {
-                    bulk_g2s32(dst, in + (uint64_t)(uint32_t)ids.x * in_stride, ROWB, bar);
-                    bulk_g2s32(dst + ROWB, in + (uint64_t)(uint32_t)ids.y * in_stride, ROWB, bar);
-                    bulk_g2s32(dst + 2 * ROWB, in + (uint64_t)(uint32_t)ids.z * in_stride, ROWB, bar);
-                    bulk_g2s32(dst + 3 * ROWB, in + (uint64_t)(uint32_t)ids.w * in_stride, ROWB, bar);
+                    bulk_g2s32(dst, in + (uint64_t)(uint32_t)ids.x * in_stride, REC, bar);
+                    bulk_g2s32(dst + REC, in + (uint64_t)(uint32_t)ids.y * in_stride, REC, bar);
+                    bulk_g2s32(dst + 2 * REC, in + (uint64_t)(uint32_t)ids.z * in_stride, REC, bar);
+                    bulk_g2s32(dst + 3 * REC, in + (uint64_t)(uint32_t)ids.w * in_stride, REC, bar);
                 }
             }
             issued += 1;
@@ -412,12 +384,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
         begin_range(a, st, s);
 
         int pos = 0;
-        // hop-1 shortcut: lanes 0..3 fetch the (slot, rank) of the group's neighbours one group ahead
-        uint32_t reg_next = 0;
-        if (HOP1 && lane < G && lane < n_pos) reg_next = __ldg(a.hop0_hll + __ldg(ids_ptr + lane));
         for (int g = 0; g < n_groups; ++g) {
-            const uint32_t reg_cur = reg_next;
-            if (HOP1 && lane < G && (g + 1) * G + lane < n_pos) reg_next = __ldg(a.hop0_hll + __ldg(ids_ptr + (g + 1) * G + lane));
             mbar_wait32(bars + 8 * slot_c, par_c);
             const int cnt = min(G, n_pos - g * G);
             const uint32_t rows = ring + slot_c * STAGE + lane * 16;
@@ -429,28 +396,17 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
                     advance_row(a, st, s);
                 }
                 if (l + 1 < cnt && pos + 1 < st.re) {
-                    const uint4 m1 = lds_u4(rows + l * ROWB);
-                    const uint4 m2 = lds_u4(rows + (l + 1) * ROWB);
-                    if (HOP1) {
-                        acc_merge_mh2(st, m1, m2);
-                        acc_merge_reg(st, __shfl_sync(FULL, reg_cur, l), lane);
-                        acc_merge_reg(st, __shfl_sync(FULL, reg_cur, l + 1), lane);
-                    } else {
-                        const uint2 h1 = lds_u2(rows_h + l * ROWB);
-                        const uint2 h2 = lds_u2(rows_h + (l + 1) * ROWB);
-                        acc_merge2(st, m1, h1, m2, h2);
-                    }
+                    const uint4 m1 = lds_u4(rows + l * REC);
+                    const uint2 h1 = lds_u2(rows_h + l * REC);
+                    const uint4 m2 = lds_u4(rows + (l + 1) * REC);
+                    const uint2 h2 = lds_u2(rows_h + (l + 1) * REC);
+                    acc_merge2(st, m1, h1, m2, h2);
                     l += 2;
                     pos += 2;
                 } else {
-                    const uint4 m1 = lds_u4(rows + l * ROWB);
-                    if (HOP1) {
-                        acc_merge_mh(st, m1);
-                        acc_merge_reg(st, __shfl_sync(FULL, reg_cur, l), lane);
-                    } else {
-                        const uint2 h1 = lds_u2(rows_h + l * ROWB);
-                        acc_merge(st, m1, h1);
-                    }
+                    const uint4 m1 = lds_u4(rows + l * REC);
+                    const uint2 h1 = lds_u2(rows_h + l * REC);
+                    acc_merge(st, m1, h1);
                     l += 1;
                     pos += 1;
                 }
@@ -674,7 +630,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D map over [n_rows x 192 uint32] with row pitch `stride` bytes; box = one row (gather4 fetches 4 boxes)
-static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_rows, int64_t stride, int box_cols) {
+static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_rows, int64_t stride) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -682,7 +638,7 @@ static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_row
     }
     cuuint64_t dims[2] = {(cuuint64_t)(REC / 4), (cuuint64_t)n_rows};
     cuuint64_t strides[1] = {(cuuint64_t)stride};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};
+    cuuint32_t box[2] = {(cuuint32_t)(REC / 4), 1};
     cuuint32_t elem[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, elem,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -696,10 +652,10 @@ static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_row
 }
 
 // TMA engine configurations: (stages, warps per CTA, CTAs per SM).  Shared memory per warp = stages * 3 KB.
-template <int S, int WARPS, int MIN_CTAS, bool GATHER4, bool HOP1>
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4>
 static int launch_tma(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
-    constexpr size_t smem = (size_t)WARPS * S * 4 * (HOP1 ? REC_MH : REC) + WARPS * S * 8;
-    auto k = merge_tma_kernel<S, WARPS, MIN_CTAS, GATHER4, HOP1>;
+    constexpr size_t smem = (size_t)WARPS * S * 4 * REC + WARPS * S * 8;
+    auto k = merge_tma_kernel<S, WARPS, MIN_CTAS, GATHER4>;
     SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = 0, rc;
     if ((rc = resident_grid(k, WARPS * 32, smem, &grid)) != SS_OK) return rc;
@@ -718,14 +674,14 @@ static int tma_config(int64_t nnz) {
     return nnz >= (1ll << 28) ? 0 : 1;
 }
 
-template <bool GATHER4, bool HOP1>
+template <bool GATHER4>
 static int launch_tma_cfg(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
     switch (tma_config(a.nnz)) {
-        case 0: return launch_tma<4, 4, 4, GATHER4, HOP1>(a, tmap, st);   // 16 warps / SM, 4 stages
-        case 2: return launch_tma<2, 4, 8, GATHER4, HOP1>(a, tmap, st);   // 32 warps / SM, 2 stages
-        case 3: return launch_tma<6, 4, 3, GATHER4, HOP1>(a, tmap, st);   // 12 warps / SM, 6 stages
-        case 4: return launch_tma<3, 8, 3, GATHER4, HOP1>(a, tmap, st);   // 24 warps / SM, 3 stages, 8-warp CTAs
-        default: return launch_tma<3, 4, 6, GATHER4, HOP1>(a, tmap, st);  // 24 warps / SM, 3 stages
+        case 0: return launch_tma<4, 4, 4, GATHER4>(a, tmap, st);   // 16 warps / SM, 4 stages
+        case 2: return launch_tma<2, 4, 8, GATHER4>(a, tmap, st);   // 32 warps / SM, 2 stages
+        case 3: return launch_tma<6, 4, 3, GATHER4>(a, tmap, st);   // 12 warps / SM, 6 stages
+        case 4: return launch_tma<3, 8, 3, GATHER4>(a, tmap, st);   // 24 warps / SM, 3 stages, 8-warp CTAs
+        default: return launch_tma<3, 4, 6, GATHER4>(a, tmap, st);  // 24 warps / SM, 3 stages
     }
 }
 
@@ -749,15 +705,14 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
                   ss_stream_t stream) {
     return ss_khop_merge_peers(rowptr, colidx, n_rows, nnz, rec_in, in_rows, in_stride, rec_out, out_stride, num_perm, hll_p,
                                workspace, workspace_bytes, cards_out, cards_stride, hc, variant, 0, nullptr, nullptr, nullptr,
-                               nullptr, nullptr, stream);
+                               nullptr, stream);
 }
 
 int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
                         int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p,
                         void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
                         const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
-                        float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, const uint16_t *hop0_hll,
-                        ss_stream_t stream) {
+                        float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n_rows >= 0 && nnz >= 0 && in_rows >= 0, "negative size passed to ss_khop_merge");
@@ -809,7 +764,6 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
     a.cards = cards_out; a.cards_stride = cards_stride; a.h = hd;
     SS_REQUIRE(!mc_rec_out || (((uintptr_t)mc_rec_out & 15) == 0 && (!cards_out || mc_cards_out)),
                "multicast table must be 16-byte aligned and come with a multicast cards pointer");
-    a.hop0_hll = (variant == SS_MERGE_TMA || variant == SS_MERGE_BULK) ? hop0_hll : nullptr;  // other engines read full rows
     a.mc_out = (uint8_t *)mc_rec_out;
     a.mc_cards = mc_rec_out ? mc_cards_out : nullptr;
     a.n_peers = n_peers;
@@ -829,13 +783,12 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
         if (variant == SS_MERGE_TMA || variant == SS_MERGE_BULK) {
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof(tmap));
-            const bool hop1 = a.hop0_hll != nullptr;
             if (variant == SS_MERGE_TMA) {
                 // rows addressed by colidx are < 2^31; the map covers every row the caller's table can hold
-                if ((rc = ss::make_row_gather_map(&tmap, rec_in, in_rows, in_stride, hop1 ? 128 : 192)) != SS_OK) return rc;
-                rc = hop1 ? ss::launch_tma_cfg<true, true>(a, tmap, st) : ss::launch_tma_cfg<true, false>(a, tmap, st);
+                if ((rc = ss::make_row_gather_map(&tmap, rec_in, in_rows, in_stride)) != SS_OK) return rc;
+                rc = ss::launch_tma_cfg<true>(a, tmap, st);
             } else {
-                rc = hop1 ? ss::launch_tma_cfg<false, true>(a, tmap, st) : ss::launch_tma_cfg<false, false>(a, tmap, st);
+                rc = ss::launch_tma_cfg<false>(a, tmap, st);
             }
             if (rc != SS_OK) return rc;
         } else if (variant == SS_MERGE_LDG) {

@@ -240,9 +240,8 @@ class ShardedElphHashes(object):
             self.bounds, self.local_nnz = bounds, nnz
             lo, hi = bounds[r], bounds[r + 1]
             rec0 = torch.empty((num_nodes, rb), dtype=torch.uint8, device=device)
-            hop0_hll = eh._hop0_side_table(num_nodes, device)
             ev = eh._event_begin(device)
-            eh._init_records(num_nodes, device, out=rec0, hop0_hll=hop0_hll)  # hop 0 is cheap: redundant, no exchange
+            eh._init_records(num_nodes, device, out=rec0)  # hop 0 is cheap: computed redundantly, no exchange
             eh._event_end('init_records', ev, device)
             ws = None
             if symm is not None:
@@ -263,8 +262,7 @@ class ShardedElphHashes(object):
                         t0 = torch.cuda.Event(enable_timing=True)
                         t0.record()
                         ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
-                                       ws, peer_recs, peer_cards, mc_rec, mc_cards,
-                                       hop0_hll=hop0_hll if k == 1 else None)
+                                       ws, peer_recs, peer_cards, mc_rec, mc_cards)
                         t1 = torch.cuda.Event(enable_timing=True)
                         t1.record()
                         self._merge_events.append((t0, t1))
@@ -279,7 +277,7 @@ class ShardedElphHashes(object):
                         t0 = torch.cuda.Event(enable_timing=True)
                         t0.record()
                         ws = eh._merge(rowptr, colidx, nnz, recs[k - 1], recs[k][lo:hi], cards[lo:hi, k - 1], device,
-                                       ws, hop0_hll=hop0_hll if k == 1 else None)
+                                       ws)
                         t1 = torch.cuda.Event(enable_timing=True)
                         t1.record()
                         self._merge_events.append((t0, t1))

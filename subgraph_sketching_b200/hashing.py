@@ -378,7 +378,6 @@ class ElphHashes(object):
         self.hll_prop = HllPropagation(self)
         self.merge_variant = merge_variant
         self.validate_links = True  # bounds-check link endpoints (the reference raises IndexError)
-        self.hop1_shortcut = True   # hop 1 gathers only the MinHash half of the hop-0 records (+ 2-byte side table)
         self.event_log = None  # set to a list to record (name, start_event, end_event) around kernels
         # linear-counting table, evaluated with the reference's own float32 torch expression (hashing.py:195)
         nz = torch.arange(1, self.m + 1, dtype=torch.int64)
@@ -444,21 +443,14 @@ class ElphHashes(object):
         return ab
 
     # ------------------------------------------------------------------ K1
-    def _init_records(self, n_nodes, device, first_id=1, out=None, hop0_hll=None):
-        """hop-0 records; hop0_hll (int16 [n], optional): side table (slot << 8 | rank) for the hop-1 shortcut"""
+    def _init_records(self, n_nodes, device, first_id=1, out=None):
         d = self._consts(device)
         rb = self._record_bytes()
         rec = out if out is not None else torch.empty((n_nodes, rb), dtype=torch.uint8, device=device)
         check(lib.ss_init_records(n_nodes, first_id, self.num_perm, self.p, _ptr(d['perm_a']), _ptr(d['perm_b']),
-                                  _ptr(d['window']), _ptr(rec), rec.stride(0) if n_nodes else rb, _ptr(hop0_hll),
+                                  _ptr(d['window']), _ptr(rec), rec.stride(0) if n_nodes else rb,
                                   _stream_ptr(device)), 'ss_init_records')
         return rec
-
-    def _hop0_side_table(self, n_nodes, device):
-        """int16 [n] buffer for the hop-1 shortcut, or None when the shortcut does not apply"""
-        if self.hop1_shortcut and self.num_perm == 128 and self.p == 8 and self.merge_variant in ('auto', 'tma', 'bulk'):
-            return torch.empty(max(n_nodes, 1), dtype=torch.int16, device=device)
-        return None
 
     def initialise_minhash(self, n_nodes):
         """hop-0 MinHash signatures, int64 [n, P] on the CPU like the reference (hashing.py:118-124)"""
@@ -476,7 +468,7 @@ class ElphHashes(object):
 
     # ------------------------------------------------------------------ K2
     def _merge(self, rowptr, colidx, nnz, rec_in, rec_out, cards_col, device, ws=None, peer_recs=None,
-               peer_cards=None, mc_rec=0, mc_cards=0, hop0_hll=None):
+               peer_cards=None, mc_rec=0, mc_cards=0):
         """one hop over the rows of `rec_out`; peer_recs / peer_cards: device addresses (ints) of the peers'
         copies of rec_out / cards_col for the fused multi-GPU exchange (ss_khop_merge_peers)"""
         d = self._consts(device)
@@ -486,7 +478,7 @@ class ElphHashes(object):
             ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
         ev = self._event_begin(device)
         n_peers = len(peer_recs) if peer_recs else 0
-        if n_peers or mc_rec or hop0_hll is not None:
+        if n_peers or mc_rec:
             pr = (ctypes.c_void_p * max(n_peers, 1))(*(peer_recs or [0]))
             pc = (ctypes.c_void_p * max(n_peers, 1))(*(peer_cards or [0] * max(n_peers, 1)))
             check(lib.ss_khop_merge_peers(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0],
@@ -494,7 +486,7 @@ class ElphHashes(object):
                                           _ptr(ws), ws.numel(), _ptr(cards_col),
                                           cards_col.stride(0) if cards_col is not None else 0, ctypes.byref(d['hc']),
                                           _lib.MERGE_VARIANTS[self.merge_variant], n_peers, pr, pc,
-                                          ctypes.c_void_p(mc_rec), ctypes.c_void_p(mc_cards), _ptr(hop0_hll),
+                                          ctypes.c_void_p(mc_rec), ctypes.c_void_p(mc_cards),
                                           _stream_ptr(device)), 'ss_khop_merge_peers')
         else:
             check(lib.ss_khop_merge(_ptr(rowptr), _ptr(colidx), n_rows, nnz, _ptr(rec_in), rec_in.shape[0],
@@ -563,16 +555,14 @@ class ElphHashes(object):
             cards = torch.zeros((num_nodes, self.max_hops), dtype=torch.float32, device=device)
             recs = [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(self.max_hops + 1)]
             ws = None
-            hop0_hll = self._hop0_side_table(num_nodes, device)
             for k in range(self.max_hops + 1):
                 logger.info(f"Calculating hop {k} hashes")
                 if k == 0:
                     ev = self._event_begin(device)
-                    self._init_records(num_nodes, device, out=recs[0], hop0_hll=hop0_hll)
+                    self._init_records(num_nodes, device, out=recs[0])
                     self._event_end('init_records', ev, device)
                 elif num_nodes > 0:
-                    ws = self._merge(rowptr, colidx, nnz, recs[k - 1], recs[k], cards[:, k - 1], device, ws,
-                                     hop0_hll=hop0_hll if k == 1 else None)
+                    ws = self._merge(rowptr, colidx, nnz, recs[k - 1], recs[k], cards[:, k - 1], device, ws)
             logger.info(f'hash generation enqueued in {time() - start} s')
             tables = SketchTables({k: HopSketch(recs[k], self.num_perm, self.p, out_device)
                                    for k in range(self.max_hops + 1)}, self.num_perm, self.p)

@@ -554,18 +554,3 @@ def test_cache_round_trip_in_reference_formats(tmp_path):
     ok, err = float_close(f1, blob['features_zo0_fl1'], link_scale(blob['links'], blob['cards']))
     assert ok, err
     assert cache.generate_file_names(root, 'train', 2, 5)[0].endswith('train_negs5_subgraph_featurecache.pt')
-
-
-def test_hop1_shortcut_is_bit_identical():
-    """hop 1 with the MinHash-only gather + 2-byte side table vs the full-record gather, gather4 and bulk engines"""
-    n = 1 << 13
-    ei = rmat_edges(13, 16, 4).to(DEV)
-    for variant in ('tma', 'bulk'):
-        a = ssb.ElphHashes(make_args(2), merge_variant=variant)
-        b = ssb.ElphHashes(make_args(2), merge_variant=variant)
-        b.hop1_shortcut = False
-        ta, ca = a.build_hash_tables(n, ei)
-        tb, cb = b.build_hash_tables(n, ei)
-        for k in range(3):
-            assert torch.equal(ta.records(k), tb.records(k)), (variant, k)
-        assert torch.equal(ca, cb)

@@ -18,15 +18,14 @@ ei = rmat_edges(scale, ef, 0, dev)
 eh = ssb.ElphHashes(Namespace(max_hash_hops=1, floor_sf=False, minhash_num_perm=128, hll_p=8, use_zero_one=False))
 rowptr, colidx, nnz, _ = ssb.build_csr(ei, dev, num_rows=n, add_loops=True)
 del ei
-hop0 = eh._hop0_side_table(n, dev)
-rec0 = eh._init_records(n, dev, hop0_hll=hop0)
+rec0 = eh._init_records(n, dev)
 rec1 = torch.empty_like(rec0)
 rec2 = torch.empty_like(rec0)
 cards = torch.zeros((n, 1), device=dev)
 bytes_alg = nnz * 768 + n * 768 + 4 * nnz + 8 * (n + 1) + 4 * n
 print(f'scale {scale}: N={n} nnz={nnz} algorithmic bytes/hop = {bytes_alg / 1e9:.1f} GB')
 ref = None
-runs = [('bulk', 1), ('tma', 0), ('tma', 1)]
+runs = [('ldg', None), ('bulk', 0), ('bulk', 1), ('tma', 0), ('tma', 1), ('tma', 2), ('tma', 3), ('tma', 4)]
 for variant, cfg in runs:
     if cfg is not None:
         os.environ['SS_B200_TMA_CFG'] = str(cfg)
@@ -41,19 +40,9 @@ for variant, cfg in runs:
         e.record()
         torch.cuda.synchronize()
         times.append(s.elapsed_time(e))
-    h1 = []
-    for use in (None, hop0):  # hop 1: full-record gather vs MinHash-only gather + side table
-        for _ in range(3):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            eh._merge(rowptr, colidx, nnz, rec0, rec1, cards[:, 0], dev, hop0_hll=use)
-            e.record()
-            torch.cuda.synchronize()
-        h1.append(s.elapsed_time(e))
     chk = int(rec2.view(torch.int32).sum(dtype=torch.int64)), float(cards.sum())
     if ref is None:
         ref = chk
     ms = min(times[1:])
     print(f'{variant} cfg={cfg}: {ms:.2f} ms  {bytes_alg / ms / 1e6:.0f} GB/s algorithmic  '
-          f'{"OK" if chk == ref else "MISMATCH " + str(chk) + " vs " + str(ref)}   hop 1: full {h1[0]:.2f} ms, shortcut '
-          f'{h1[1]:.2f} ms', flush=True)
+          f'{"OK" if chk == ref else "MISMATCH " + str(chk) + " vs " + str(ref)}', flush=True)
