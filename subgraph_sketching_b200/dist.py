@@ -159,17 +159,23 @@ class ShardedElphHashes(object):
         rowptr_g = torch.empty(num_nodes + 1, dtype=torch.int64, device=device)
         stats = torch.empty(4, dtype=torch.int64, device=device)
         src32 = dst32 = None
-        if zero_copy and n_edges:  # host-resident edge list: keep 32-bit device copies for the fill pass
-            src32 = torch.empty(n_edges, dtype=torch.int32, device=device)
-            dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
         st = _stream_ptr(device)
         G, r = self.world_size, self.rank
-        if G > 1 and not zero_copy and n_edges >= (1 << 10):
-            # sharded histogram pass: rank r scans only its 1/G slice of the edge list; prefix sums are linear,
-            # so the global rowptr is the SUM over ranks of the partial ones (one all-reduce) plus the self loops
-            e_lo, e_hi = (n_edges * r) // G, (n_edges * (r + 1)) // G
+        if G > 1 and n_edges >= (1 << 10):
+            # sharded first pass: rank r scans only its 1/G slice of the edge list (for a pinned HOST list that is
+            # also all it pulls over its own PCIe link).  Prefix sums are linear, so the global rowptr is the SUM
+            # over ranks of the partial ones (one all-reduce) plus the self loops; a host-resident list is
+            # re-assembled on every GPU from the 32-bit slice copies with one all-gather over NVLink.
+            per = (n_edges + G - 1) // G
+            e_lo, e_hi = min(r * per, n_edges), min((r + 1) * per, n_edges)
+            s32 = d32 = None
+            if zero_copy:
+                src32 = torch.empty(G * per, dtype=torch.int32, device=device)
+                dst32 = torch.empty(G * per, dtype=torch.int32, device=device)
+                s32, d32 = src32[r * per:], dst32[r * per:]
             check(lib.ss_csr_rowptr(_ptr(src[e_lo:e_hi]), _ptr(dst[e_lo:e_hi]), e_hi - e_lo, 0, 0, num_nodes,
-                                    _ptr(rowptr_g), None, None, _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
+                                    _ptr(rowptr_g), _ptr(s32), _ptr(d32), _ptr(stats), _ptr(ws), ws.numel(), st),
+                  'ss_csr_rowptr')
             dist.all_reduce(rowptr_g, op=dist.ReduceOp.SUM, group=self.group)
             ext = torch.stack([stats[0], -stats[3]])
             dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=self.group)
@@ -177,7 +183,13 @@ class ShardedElphHashes(object):
             n_loops = max_id + 1
             if 0 <= max_id < num_nodes:  # self loop of node i < n_loops adds 1 to every prefix entry above i
                 rowptr_g += torch.arange(num_nodes + 1, device=device, dtype=torch.int64).clamp_(max=n_loops)
+            if zero_copy:
+                dist.all_gather_into_tensor(src32, src32[r * per:(r + 1) * per].clone(), group=self.group)
+                dist.all_gather_into_tensor(dst32, dst32[r * per:(r + 1) * per].clone(), group=self.group)
         else:
+            if zero_copy and n_edges:  # host-resident edge list: keep 32-bit device copies for the fill pass
+                src32 = torch.empty(n_edges, dtype=torch.int32, device=device)
+                dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
             check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, -1, 0, num_nodes, _ptr(rowptr_g), _ptr(src32),
                                     _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
             max_id, _, n_loops, min_id = (int(v) for v in stats.tolist())

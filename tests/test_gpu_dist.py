@@ -50,6 +50,11 @@ def _worker(rank, world, port, scale, K, exchange='auto'):
         assert torch.equal(cards, c1)
         lo, hi = link_slice(links.shape[0], world, rank)
         assert torch.equal(feats, f1[lo:hi])
+        # a pinned HOST edge list: every rank pulls only its slice over PCIe, the rest arrives over NVLink
+        th, ch = sh.build_hash_tables(n, ei.cpu().pin_memory())
+        for k in range(K + 1):
+            assert torch.equal(th.records(k), t1.records(k)), f'rank {rank}: host-fed hop {k} records differ'
+        assert torch.equal(ch, c1)
         shares = [int(x) for x in sh.bounds]
         assert shares[0] == 0 and shares[-1] == n
         if world > 1:  # blocks are balanced by neighbour count: the hub block is much shorter in rows
