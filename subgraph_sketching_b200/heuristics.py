@@ -9,7 +9,6 @@ float32.  No CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes
 
 import numpy as np
 import torch
