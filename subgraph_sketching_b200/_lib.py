@@ -89,7 +89,7 @@ def _load():
 # kernels enqueued by one call of each entry point (for the bench's `gpu_launches` claim); entry points
 # that return early on empty input are counted by the caller's own bookkeeping
 KERNELS_PER_CALL = {
-    'ss_init_records': 1, 'ss_pack_records': 1, 'ss_unpack_records': 1, 'ss_csr_rowptr': 4, 'ss_csr_fill': 1,
+    'ss_init_records': 1, 'ss_pack_records': 1, 'ss_unpack_records': 1, 'ss_csr_rowptr': 4, 'ss_csr_fill': 2,
     'ss_khop_merge': 2, 'ss_khop_merge_peers': 2, 'ss_prop_min_i64': 1, 'ss_prop_max_i8': 1, 'ss_hll_count': 1, 'ss_estimate_bias': 1,
     'ss_jaccard_i64': 1, 'ss_max_i8': 1, 'ss_link_features': 1, 'ss_col_sums': 1, 'ss_common_neighbour_scores': 1,
 }

@@ -248,25 +248,33 @@ __device__ __forceinline__ float bias_6nn(const HllDev &h, float e) {
             if (__ldg(est + mid) < e) lo = mid + 1; else hi = mid;
         }
         int l = lo - 1, r = lo;
+        // two-pointer selection outwards from e.  est is monotone and float32 subtraction is monotone, so the
+        // distances on each side are non-decreasing: the picks come out in ascending (distance, index) order --
+        // exact ties between the sides go to the lower index, as a stable ascending sort would do.  The only
+        // way to leave that order is a run of equal distances on the LEFT side (duplicate table entries), which
+        // is detected and repaired by the insertion sort below (never taken with the packaged tables).
+        float dd[6];
+        bool left_run = false, prev_left = false;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             float dl = 3.4e38f, dr = 3.4e38f;
             if (l >= 0) { float d = __fsub_rn(e, __ldg(est + l)); dl = __fmul_rn(d, d); }
             if (r < h.T) { float d = __fsub_rn(e, __ldg(est + r)); dr = __fmul_rn(d, d); }
-            // on an exact tie prefer the lower index (what a stable ascending sort would do)
-            if (l >= 0 && (r >= h.T || dl <= dr)) { idx[k] = l; --l; } else { idx[k] = r; ++r; }
+            if (l >= 0 && (r >= h.T || dl <= dr)) {
+                if (k > 0 && prev_left && dl == dd[k - 1]) left_run = true;
+                idx[k] = l; dd[k] = dl; --l; prev_left = true;
+            } else {
+                idx[k] = r; dd[k] = dr; ++r; prev_left = false;
+            }
         }
-        // `idx` is in the order chosen; re-establish ascending (distance, index) order for the mean
-        // (insertion sort of 6 by distance then index)
-        float dd[6];
+        if (left_run) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { float d = __fsub_rn(e, __ldg(est + idx[k])); dd[k] = __fmul_rn(d, d); }
+            for (int a = 1; a < 6; ++a) {
 #pragma unroll
-        for (int a = 1; a < 6; ++a) {
-#pragma unroll
-            for (int b = a; b > 0; --b) {
-                bool sw = dd[b] < dd[b - 1] || (dd[b] == dd[b - 1] && idx[b] < idx[b - 1]);
-                if (sw) { float td = dd[b]; dd[b] = dd[b - 1]; dd[b - 1] = td; int ti = idx[b]; idx[b] = idx[b - 1]; idx[b - 1] = ti; }
+                for (int b = a; b > 0; --b) {
+                    bool sw = dd[b] < dd[b - 1] || (dd[b] == dd[b - 1] && idx[b] < idx[b - 1]);
+                    if (sw) { float td = dd[b]; dd[b] = dd[b - 1]; dd[b - 1] = td; int ti = idx[b]; idx[b] = idx[b - 1]; idx[b - 1] = ti; }
+                }
             }
         }
     } else {

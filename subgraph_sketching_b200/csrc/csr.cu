@@ -4,6 +4,7 @@
 // (/root/reference/src/hashing.py:148; flow source -> target, reduction at edge_index[1]).  A pull-style
 // merge needs in-neighbours per destination, so: histogram of destinations -> exclusive scan -> fill with
 // per-row cursors.  Order inside a row is arbitrary (min/max are order independent).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -186,13 +187,24 @@ __global__ void __launch_bounds__(SCAN_BLOCK) rowptr_kernel(const uint32_t *__re
     }
 }
 
-template <typename IdT>
+// fill cursors that already hold the absolute write position: cursor[r] = low 32 bits of rowptr[r]
+__global__ void __launch_bounds__(256) cursor_init_kernel(const int64_t *__restrict__ rowptr, int64_t n_rows,
+                                                           uint32_t *__restrict__ cursor) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+        cursor[r] = (uint32_t)rowptr[r];
+}
+
+// ABS_CURSOR: the cursors start at rowptr[d] (mod 2^32), so one atomic returns the write position and the random
+// 8-byte rowptr read per edge disappears (one third of the kernel's sector traffic).  When the local nnz does not
+// fit 32 bits the high part is recovered from rowptr[d] (uniform branch, whole grid takes the same side).
+template <typename IdT, bool ABS_CURSOR>
 __global__ void __launch_bounds__(256) fill_kernel(const IdT *__restrict__ src, const IdT *__restrict__ dst,
                                                     int64_t n_edges, int64_t n_self_loops_arg, const long long *stats,
                                                     int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ rowptr,
                                                     uint32_t *cursor, int32_t *__restrict__ colidx) {
     const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int64_t total = n_edges + n_rows;
+    const bool fits32 = ABS_CURSOR && (uint64_t)__ldg(rowptr + n_rows) < (1ull << 32);
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t d, s;
         if (t < n_edges) {
@@ -204,9 +216,24 @@ __global__ void __launch_bounds__(256) fill_kernel(const IdT *__restrict__ src, 
             s = row_begin + d;
             if (s >= n_self_loops) continue;
         }
-        uint32_t k = atomicAdd(cursor + d, 1u);
-        colidx[rowptr[d] + k] = (int32_t)s;
+        const uint32_t k = atomicAdd(cursor + d, 1u);
+        if (ABS_CURSOR) {
+            if (fits32) {
+                colidx[k] = (int32_t)s;
+            } else {
+                const int64_t base = rowptr[d];
+                colidx[base + (uint32_t)(k - (uint32_t)base)] = (int32_t)s;
+            }
+        } else {
+            colidx[rowptr[d] + k] = (int32_t)s;
+        }
     }
+}
+
+// SS_B200_CSR_FILL=legacy keeps zero-based cursors + a rowptr read per edge (the first version)
+static bool abs_cursor_fill() {
+    const char *e = getenv("SS_B200_CSR_FILL");
+    return !(e && e[0] == 'l');
 }
 
 }  // namespace ss
@@ -283,17 +310,33 @@ int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, co
     SS_REQUIRE(colidx, "colidx is null");
     cudaStream_t st = (cudaStream_t)stream;
     ss::CsrWorkspace w = ss::carve(workspace, n_rows);
-    SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
     int64_t total = n_edges + n_rows;
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)ss::sm_count() * 32;
     int grid = (int)(blocks < cap ? blocks : cap);
-    if (src32 && dst32) {
-        ss::fill_kernel<int32_t><<<grid, 256, 0, st>>>(src32, dst32, n_edges, n_self_loops, (const long long *)stats, row_begin,
-                                                       n_rows, rowptr, w.deg, colidx);
+    const bool abs_cursor = ss::abs_cursor_fill();
+    if (abs_cursor) {
+        int64_t cb = (n_rows + 255) / 256;
+        ss::cursor_init_kernel<<<(int)(cb < cap ? cb : cap), 256, 0, st>>>(rowptr, n_rows, w.deg);
+        SS_LAUNCH_CHECK("cursor_init_kernel");
     } else {
-        ss::fill_kernel<int64_t><<<grid, 256, 0, st>>>(src, dst, n_edges, n_self_loops, (const long long *)stats, row_begin,
-                                                       n_rows, rowptr, w.deg, colidx);
+        SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
+    }
+    const long long *stp = (const long long *)stats;
+    if (src32 && dst32) {
+        if (abs_cursor)
+            ss::fill_kernel<int32_t, true><<<grid, 256, 0, st>>>(src32, dst32, n_edges, n_self_loops, stp, row_begin, n_rows,
+                                                                 rowptr, w.deg, colidx);
+        else
+            ss::fill_kernel<int32_t, false><<<grid, 256, 0, st>>>(src32, dst32, n_edges, n_self_loops, stp, row_begin, n_rows,
+                                                                  rowptr, w.deg, colidx);
+    } else {
+        if (abs_cursor)
+            ss::fill_kernel<int64_t, true><<<grid, 256, 0, st>>>(src, dst, n_edges, n_self_loops, stp, row_begin, n_rows,
+                                                                 rowptr, w.deg, colidx);
+        else
+            ss::fill_kernel<int64_t, false><<<grid, 256, 0, st>>>(src, dst, n_edges, n_self_loops, stp, row_begin, n_rows,
+                                                                  rowptr, w.deg, colidx);
     }
     SS_LAUNCH_CHECK("fill_kernel");
     return SS_OK;

@@ -43,6 +43,11 @@ _TABLES_PATH = os.environ.get('SS_B200_HLLPP_TABLES') or os.path.join(
     os.path.dirname(os.path.abspath(__file__)), 'data', 'hllpp_tables.npz')
 
 
+def _env_int(name, default):
+    v = os.environ.get(name)
+    return int(v) if v not in (None, '') else default
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -379,6 +384,14 @@ class ElphHashes(object):
         self.merge_variant = merge_variant
         self.validate_links = True  # bounds-check link endpoints (the reference raises IndexError)
         self.event_log = None  # set to a list to record (name, start_event, end_event) around kernels
+        # layout / scheduling knobs of build_hash_tables (defaults = measured best, profiles/r01_merge_tuning.txt):
+        #   record_stride: bytes between consecutive records of a hop table (None = compact).  1024 keeps every
+        #     768-byte record inside one 1 KB-aligned block (fewer DRAM pages per gathered row) for a third more
+        #     table memory; used only while all K+1 tables stay below `padded_tables_max_frac` of the device memory
+        #   overlap_init: hop-0 initialisation (write-bound) on a side stream under the CSR build (atomics-bound)
+        self.record_stride = _env_int('SS_B200_RECORD_STRIDE', None)
+        self.padded_tables_max_frac = 0.45
+        self.overlap_init = bool(_env_int('SS_B200_OVERLAP_INIT', 0))
         # linear-counting table, evaluated with the reference's own float32 torch expression (hashing.py:195)
         nz = torch.arange(1, self.m + 1, dtype=torch.int64)
         self._lc_host = torch.cat([torch.zeros(1), self.m * torch.log(self.m / nz)]).float()
@@ -533,6 +546,21 @@ class ElphHashes(object):
               'ss_unpack_records')
         return out
 
+    def _alloc_hop_tables(self, num_nodes, rb, device):
+        """K+1 record tables [num_nodes, rb] (uint8), row pitch = record_stride when that is set and affordable"""
+        stride = rb
+        want = self.record_stride
+        if want is not None and want > rb:
+            if want % 16:
+                raise ValueError('record_stride must be a multiple of 16')
+            total = torch.cuda.get_device_properties(device).total_memory
+            if (self.max_hops + 1) * num_nodes * want <= self.padded_tables_max_frac * total:
+                stride = want
+        if stride == rb:
+            return [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(self.max_hops + 1)]
+        return [torch.empty((num_nodes, stride), dtype=torch.uint8, device=device)[:, :rb]
+                for _ in range(self.max_hops + 1)]
+
     def build_hash_tables(self, num_nodes, edge_index):
         """
         Generate a hashing table that allows the size of the intersection of two nodes k-hop neighbours to be
@@ -546,21 +574,39 @@ class ElphHashes(object):
         out_device = edge_index.device
         with torch.cuda.device(device):
             start = time()
+            rb = self._record_bytes()
+            recs = self._alloc_hop_tables(num_nodes, rb, device)
+            main = torch.cuda.current_stream(device)
+            init_done = None
+            if self.overlap_init and num_nodes > 0:
+                # hop 0 does not depend on the graph: enqueue it first, on the side stream, so that it runs under
+                # the CSR build (which also holds the only host synchronisation of this function)
+                side = self._side_stream(device)
+                side.wait_stream(main)  # the table memory may still be in use by earlier work on this stream
+                with torch.cuda.stream(side):
+                    ev = self._event_begin(device)
+                    self._init_records(num_nodes, device, out=recs[0])
+                    self._event_end('init_records', ev, device)
+                    init_done = torch.cuda.Event()
+                    init_done.record(side)
             ev = self._event_begin(device)
-            rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=num_nodes, add_loops=True)
+            try:
+                rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=num_nodes, add_loops=True)
+            finally:  # also on the error paths: the table memory must not be recycled under the side stream
+                if init_done is not None:
+                    main.wait_event(init_done)
             self._event_end('csr_build', ev, device)
             if max_id >= num_nodes:
                 raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
-            rb = self._record_bytes()
             cards = torch.zeros((num_nodes, self.max_hops), dtype=torch.float32, device=device)
-            recs = [torch.empty((num_nodes, rb), dtype=torch.uint8, device=device) for _ in range(self.max_hops + 1)]
             ws = None
             for k in range(self.max_hops + 1):
                 logger.info(f"Calculating hop {k} hashes")
                 if k == 0:
-                    ev = self._event_begin(device)
-                    self._init_records(num_nodes, device, out=recs[0])
-                    self._event_end('init_records', ev, device)
+                    if init_done is None:
+                        ev = self._event_begin(device)
+                        self._init_records(num_nodes, device, out=recs[0])
+                        self._event_end('init_records', ev, device)
                 elif num_nodes > 0:
                     ws = self._merge(rowptr, colidx, nnz, recs[k - 1], recs[k], cards[:, k - 1], device, ws)
             logger.info(f'hash generation enqueued in {time() - start} s')
