@@ -121,7 +121,7 @@ def main():
     print('hll_count_p8 written')
 
 
-if __name__ == '__main__' and 'heuristics' not in sys.argv:
+if __name__ == '__main__' and 'heuristics' not in sys.argv and 'sign' not in sys.argv:
     main()
 
 
@@ -169,3 +169,61 @@ def heuristics_golden():
 
 if __name__ == '__main__' and 'heuristics' in sys.argv:
     heuristics_golden()
+
+
+def sign_cases():
+    """(name, x, edge_index, edge_weight, sign_k): unit weights / integer weights with duplicate edges, duplicate
+    self loops and isolated tail nodes / float weights; feature widths on both kernel paths (multiple of 4 or
+    not, one or several 128-column tiles)"""
+    g = torch.Generator().manual_seed(21)
+    out = []
+    ei = barabasi_albert(300, 8, 1)
+    out.append(('ba300_unit_f16', torch.rand(300, 16, generator=g), ei, torch.ones(ei.shape[1], dtype=torch.int64), (0, 2)))
+    ei = torch.randint(0, 150, (2, 1500), generator=g)
+    ei[:, :40] = torch.randint(0, 20, (1, 40), generator=g).repeat(2, 1)  # self loops, several per node
+    out.append(('multi_int_f7', torch.randn(180, 7, generator=g), ei, torch.randint(1, 4, (1500,), generator=g), (0, 3)))
+    ei = torch.randint(0, 400, (2, 6000), generator=g)
+    out.append(('float_w_f130', torch.randn(400, 130, generator=g), ei, torch.rand(6000, generator=g) + 0.1, (1,)))
+    ei = barabasi_albert(200, 5, 3)
+    out.append(('ba200_unit_f256', torch.randn(200, 256, generator=g), ei, torch.ones(ei.shape[1]), (1,)))
+    return out
+
+
+def sign_golden():
+    """SIGN pre-propagation through the UNMODIFIED HashDataset._generate_sign_features
+    (/root/reference/src/datasets/elph.py:87-110).  torch_geometric / torch_sparse are absent from this image:
+    gcn_norm and spmm are served by oracle/sign_oracle.py's restatements (see its header: that part is unpinned)."""
+    import importlib
+    import types
+    from oracle import sign_oracle
+    ref_loader.load()
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    importlib.import_module('torch_geometric')
+    mod('torch_geometric.data', Dataset=object)
+    mod('torch_geometric.nn.conv')
+    mod('torch_geometric.nn.conv.gcn_conv', gcn_norm=sign_oracle.gcn_norm)
+    mod('torch_sparse', spmm=sign_oracle.spmm, coalesce=None)
+    ds = importlib.import_module('src.datasets.elph')
+    blob = {}
+    for name, x, ei, w, ks in sign_cases():
+        blob[f'{name}_x'] = x.numpy()
+        blob[f'{name}_edge_index'] = ei.numpy()
+        blob[f'{name}_weight'] = w.numpy()
+        for k in ks:
+            data = types.SimpleNamespace(x=x)
+            got = ds.HashDataset._generate_sign_features(None, data, ei, w, k)
+            assert torch.equal(got, sign_oracle.sign_features(x, ei, w, k))
+            blob[f'{name}_k{k}'] = got.numpy()
+    np.savez_compressed(os.path.join(OUT_DIR, 'sign.npz'), **blob)
+    print('sign written', os.path.getsize(os.path.join(OUT_DIR, 'sign.npz')))
+
+
+if __name__ == '__main__' and 'sign' in sys.argv:
+    sign_golden()

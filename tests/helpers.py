@@ -8,7 +8,7 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 GRAPH_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
-                     if not os.path.basename(p).startswith(('hll_count', 'heuristics')))
+                     if not os.path.basename(p).startswith(('hll_count', 'heuristics', 'sign')))
 
 
 def load_golden(name):

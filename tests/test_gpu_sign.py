@@ -1,0 +1,105 @@
+"""GPU parity of the SIGN pre-propagation against tests/golden/sign.npz -- outputs of the
+UNMODIFIED reference method HashDataset._generate_sign_features (oracle/make_golden.py sign) -- and against
+the oracle restatement on a larger power-law graph.
+
+Tolerance: float32 everywhere, every product rounded like the reference's; only the order of the per-row sum
+differs (the CSR is built with atomics), so |got - want| <= 1e-5 * max(1, sum_e |w_e x_e|) -- bounded here by
+1e-5 * max(1, max|want| of the row) for these well-conditioned inputs."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rmat_edges
+from oracle import sign_oracle
+from subgraph_sketching_b200 import sign as bs
+
+pytestmark = pytest.mark.gpu
+
+CASES = [('ba300_unit_f16', (0, 2)), ('multi_int_f7', (0, 3)), ('float_w_f130', (1,)), ('ba200_unit_f256', (1,))]
+
+
+def _close(got, want, tol=1e-5):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))
+    err = np.abs(got - want) / scale
+    return bool((err <= tol).all()), float(err.max()) if err.size else 0.0
+
+
+@pytest.mark.parametrize('name,ks', CASES)
+def test_sign_features_vs_reference_golden(name, ks):
+    blob = load_golden('sign')
+    x = torch.from_numpy(blob[f'{name}_x'])
+    ei = torch.from_numpy(blob[f'{name}_edge_index'])
+    w = torch.from_numpy(blob[f'{name}_weight'])
+    for k in ks:
+        want = blob[f'{name}_k{k}']
+        got = bs.sign_features(x, ei, w, k)                      # CPU in -> CPU out (BUDDY preprocessing)
+        assert not got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == want.shape
+        ok, err = _close(got.numpy(), want)
+        assert ok, (name, k, err)
+        got_d = bs.sign_features(x.cuda(), ei.cuda(), w.cuda(), k)  # device in -> device out
+        assert got_d.is_cuda and torch.equal(got_d.cpu()[:, :x.shape[1]], got[:, :x.shape[1]])
+        ok, err = _close(got_d.cpu().numpy(), want)
+        assert ok, (name, k, err)
+        if k > 0:  # block 0 is x itself, blocks 1..k are identical (the reference re-propagates data.x)
+            F = x.shape[1]
+            assert torch.equal(got[:, :F], x)
+            for b in range(2, k + 1):
+                assert torch.equal(got[:, b * F:(b + 1) * F], got[:, F:2 * F])
+
+
+def test_gcn_norm_coefficients_match_oracle():
+    blob = load_golden('sign')
+    ei = torch.from_numpy(blob['multi_int_f7_edge_index'])
+    w = torch.from_numpy(blob['multi_int_f7_weight'])
+    n = 180
+    dinv, loop_w = bs.gcn_norm_coefficients(ei, w, n, device='cuda')
+    ei2, w2 = sign_oracle.gcn_norm(ei, w.float(), n)
+    # the oracle's edge list ends with one loop per node: its normalised weight is dinv^2 * loop weight
+    loops = w2[-n:]
+    want = (dinv.cpu() * loop_w.cpu()) * dinv.cpu()
+    assert torch.equal(want, loops)   # integer weights: degrees are exact, so this is bit-exact
+    assert float(loop_w.min()) >= 1.0 and int((loop_w != 1).sum()) > 0  # kept self-loop weights
+
+
+def test_sign_powerlaw_vs_oracle_and_edge_cases():
+    n = 1 << 13
+    ei = rmat_edges(13, 16, 4)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(n, 128, generator=g)
+    w = torch.ones(ei.shape[1])
+    want = sign_oracle.sign_features(x, ei, w, 3)
+    got = bs.sign_features(x.cuda(), ei.cuda(), None, 3).cpu()   # edge_weight None = ones
+    ok, err = _close(got.numpy(), want.numpy())
+    assert ok, err
+    # a graph without edges: every node only has its fill-value self loop -> A = I
+    x0 = torch.randn(10, 5, generator=g)
+    out = bs.sign_features(x0, torch.zeros((2, 0), dtype=torch.int64), torch.zeros(0), 0)
+    assert torch.equal(out, x0)
+    with pytest.raises(IndexError):
+        bs.sign_features(x0, torch.tensor([[0], [10]]), torch.ones(1), 0)
+    with pytest.raises(ValueError):
+        bs.sign_features(x0, torch.tensor([[0], [1]]), torch.ones(2), 0)
+    # same signature as the reference method: (data, edge_index, edge_weight, sign_k)
+    data = types.SimpleNamespace(x=x0)
+    e1 = torch.tensor([[0, 1, 2], [1, 2, 0]])
+    a = bs.generate_sign_features(data, e1, torch.ones(3, dtype=torch.int64), 1)
+    b = sign_oracle.sign_features(x0, e1, torch.ones(3, dtype=torch.int64), 1)
+    assert _close(a.numpy(), b.numpy())[0]
+
+
+def test_sign_feature_cache_names_and_round_trip(tmp_path):
+    assert bs.feature_cache_name('r', 'train', 0) == 'r_train_featurecache.pt'
+    assert bs.feature_cache_name('r', 'valid', 3) == 'r_valid_k3_featurecache.pt'
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(50, 8, generator=g)
+    ei = torch.randint(0, 50, (2, 300), generator=g)
+    data = types.SimpleNamespace(x=x)
+    root = os.path.join(str(tmp_path), 'ds')
+    first = bs.preprocess_node_features(data, ei, torch.ones(300), 2, root=root, split='train', load_features=True)
+    assert os.path.exists(f'{root}_train_k2_featurecache.pt')
+    again = bs.preprocess_node_features(data, ei, torch.ones(300), 2, root=root, split='train', load_features=True)
+    assert torch.equal(first, again)

@@ -130,3 +130,31 @@ def test_heuristics_oracle_matches_reference_golden():
         for kind in ('cn', 'aa', 'ra'):
             got = ho.scores(A, blob[f'{name}_links'], kind)
             assert np.array_equal(got.numpy(), blob[f'{name}_{kind}']), (name, kind)
+
+
+def test_sign_oracle_matches_reference_golden_and_scipy():
+    """SIGN pre-propagation: the restatement is bit-equal to what the unmodified
+    HashDataset._generate_sign_features produced (tests/golden/sign.npz) and agrees with the textbook
+    D^-1/2 (A + I) D^-1/2 x evaluated by scipy in float64"""
+    import scipy.sparse as ssp
+    from oracle import sign_oracle
+    blob = load_golden('sign')
+    for name, ks in [('ba300_unit_f16', (0, 2)), ('multi_int_f7', (0, 3)), ('float_w_f130', (1,)),
+                     ('ba200_unit_f256', (1,))]:
+        x = torch.from_numpy(blob[f'{name}_x'])
+        ei = torch.from_numpy(blob[f'{name}_edge_index'])
+        w = torch.from_numpy(blob[f'{name}_weight'])
+        n = x.shape[0]
+        for k in ks:
+            assert torch.equal(sign_oracle.sign_features(x, ei, w, k), torch.from_numpy(blob[f'{name}_k{k}']))
+        r, c, wv = ei[0].numpy(), ei[1].numpy(), w.numpy().astype(np.float64)
+        m = r != c
+        loop_w = np.ones(n)
+        for i, v in zip(r[~m], wv[~m]):
+            loop_w[i] = v  # the last self loop of a node keeps its weight
+        A = ssp.csr_matrix((wv[m], (r[m], c[m])), shape=(n, n)) + ssp.diags(loop_w)
+        deg = np.asarray(A.sum(axis=0)).flatten()
+        dinv = np.where(deg > 0, deg ** -0.5, 0.0)
+        want = (ssp.diags(dinv) @ A @ ssp.diags(dinv)) @ x.numpy().astype(np.float64)
+        got = sign_oracle.sign_features(x, ei, w, 0).numpy()
+        assert np.abs(got - want).max() < 5e-6
