@@ -640,9 +640,16 @@ static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_row
     cuuint64_t strides[1] = {(cuuint64_t)stride};
     cuuint32_t box[2] = {(cuuint32_t)(REC / 4), 1};
     cuuint32_t elem[2] = {1, 1};
+    // L2 promotion = granularity of the L2 fills behind the gather (tuning knob SS_B200_TMA_L2PROMO = 0 / 64 / 128 / 256)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (const char *e = getenv("SS_B200_TMA_L2PROMO")) {
+        const int v = atoi(e);
+        promo = v >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                         : (v >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                     : (v >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
+    }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, elem,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld stride=%lld)", (int)r, (long long)n_rows,
                   (long long)stride);

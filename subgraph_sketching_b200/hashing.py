@@ -387,10 +387,12 @@ class ElphHashes(object):
         # layout / scheduling knobs of build_hash_tables (defaults = measured best, profiles/r01_merge_tuning.txt):
         #   record_stride: bytes between consecutive records of a hop table (None = compact).  1024 keeps every
         #     768-byte record inside one 1 KB-aligned block (fewer DRAM pages per gathered row) for a third more
-        #     table memory; used only while all K+1 tables stay below `padded_tables_max_frac` of the device memory
+        #     table memory; used only for tables of at least `padded_tables_min_nodes` rows (below that the tables
+        #     are L2-sized anyway) while all K+1 of them stay below `padded_tables_max_frac` of the device memory
         #   overlap_init: hop-0 initialisation (write-bound) on a side stream under the CSR build (atomics-bound)
         self.record_stride = _env_int('SS_B200_RECORD_STRIDE', None)
         self.padded_tables_max_frac = 0.45
+        self.padded_tables_min_nodes = 1 << 20
         self.overlap_init = bool(_env_int('SS_B200_OVERLAP_INIT', 0))
         # linear-counting table, evaluated with the reference's own float32 torch expression (hashing.py:195)
         nz = torch.arange(1, self.m + 1, dtype=torch.int64)
@@ -550,7 +552,7 @@ class ElphHashes(object):
         """K+1 record tables [num_nodes, rb] (uint8), row pitch = record_stride when that is set and affordable"""
         stride = rb
         want = self.record_stride
-        if want is not None and want > rb:
+        if want is not None and want > rb and num_nodes >= self.padded_tables_min_nodes:
             if want % 16:
                 raise ValueError('record_stride must be a multiple of 16')
             total = torch.cuda.get_device_properties(device).total_memory

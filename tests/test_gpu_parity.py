@@ -554,3 +554,39 @@ def test_cache_round_trip_in_reference_formats(tmp_path):
     ok, err = float_close(f1, blob['features_zo0_fl1'], link_scale(blob['links'], blob['cards']))
     assert ok, err
     assert cache.generate_file_names(root, 'train', 2, 5)[0].endswith('train_negs5_subgraph_featurecache.pt')
+
+
+def test_layout_and_scheduling_knobs_are_bit_equal(monkeypatch):
+    """build_hash_tables knobs (padded 1024-byte record stride, hop-0 initialisation on a side stream under the
+    CSR build, legacy zero-based CSR cursors) change layout / scheduling only: tables, cards and features stay
+    bit-identical, strided tables unpack / pickle like compact ones"""
+    n, K = 1 << 14, 3
+    dev = torch.device(DEV)
+    ei = rmat_edges(14, 16, 5, dev)
+    g = torch.Generator().manual_seed(2)
+    links = torch.randint(0, n, (50_000, 2), generator=g).to(dev)
+    base = ssb.ElphHashes(make_args(K))
+    base.record_stride, base.overlap_init = None, False
+    t0, c0 = base.build_hash_tables(n, ei)
+    f0 = base.get_subgraph_features(links, t0, c0)
+    for stride, overlap, fill in ((1024, False, 'abs'), (None, True, 'abs'), (1024, True, 'abs'), (896, True, 'legacy')):
+        monkeypatch.setenv('SS_B200_CSR_FILL', fill)
+        eh = ssb.ElphHashes(make_args(K))
+        eh.record_stride, eh.overlap_init, eh.padded_tables_min_nodes = stride, overlap, 0
+        for _ in range(2):  # twice: the second build recycles the first one's memory under the side stream
+            t1, c1 = eh.build_hash_tables(n, ei)
+        if stride:
+            assert t1.records(1).stride(0) == stride and t1.records(1).shape[1] == 768
+        for k in range(K + 1):
+            assert torch.equal(t1.records(k), t0.records(k)), (stride, overlap, fill, k)
+        assert torch.equal(c1, c0)
+        assert torch.equal(eh.get_subgraph_features(links, t1, c1), f0)
+        assert torch.equal(t1[2]['minhash'], t0[2]['minhash']) and torch.equal(t1[K]['hll'], t0[K]['hll'])
+    buf = io.BytesIO()
+    torch.save(t1, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=True)
+    assert torch.equal(back[1]['minhash'], t0[1]['minhash'].cpu())
+    with pytest.raises(ValueError):
+        eh.record_stride = 1000
+        eh.build_hash_tables(n, ei)
