@@ -227,20 +227,25 @@ int ss_common_neighbour_scores(const int64_t *rowptr, const int32_t *colidx, con
  * (PyG gcn_norm: add_remaining_self_loops with fill 1 -- an existing self loop keeps its weight, the last one
  * if there are several --, deg = sum of weights at edge_index[1], w = deg^-1/2[row] * w * deg^-1/2[col], inf -> 0;
  * torch_sparse.spmm: out[row] += w * x[col].)  The normalised edge list is never materialised:
- *   ss_gcn_norm   : dinv_out[i] = deg^-1/2 (0 where deg = 0), loop_weight_out[i] = weight of node i's self loop
+ *   ss_gcn_norm   : dinv_out[i] = deg^-1/2 (0 where deg = 0), loop_weight_out[i] = weight of node i's self loop;
+ *                   flags_out (device int32 or NULL): bit 0 = row[] is not sorted (non-decreasing), bit 1 = an id is
+ *                   outside [0, n_nodes) (such edges are ignored; the reference would fail in torch indexing)
  *   ss_sign_fill  : perm_out[rowptr[r] .. rowptr[r+1]) = positions e of the edges with row[e] = r, where rowptr is
  *                   ss_csr_rowptr(src = col, dst = row, n_self_loops = 0) -- a CSR of EDGE POSITIONS keyed by the
- *                   spmm row, so arbitrary edge weights need no permuted copy
+ *                   spmm row, so arbitrary edge weights need no permuted copy.  Not needed when row[] is sorted:
+ *                   pass perm = NULL to ss_sign_spmm, the CSR is the edge list itself and every row is summed in
+ *                   edge order like the reference's sequential scatter-add (bit-identical results)
  *   ss_sign_spmm  : out[i, k*F + f] = sum_e (dinv[i] * w_e) * dinv[col_e] * x[col_e, f] + (dinv[i] * loop_w[i]) * dinv[i] * x[i, f]
  *                   for k = 0..copies-1 (the reference concatenates sign_k identical blocks: it re-propagates
  *                   data.x every time, elph.py:104-107), float32, every product and sum rounded separately
- * row / col int64 [n_edges] = edge_index[0] / edge_index[1] (ids in [0, n_nodes): validated by the caller),
+ * row / col int64 [n_edges] = edge_index[0] / edge_index[1] (ids in [0, n_nodes): see flags_out),
  * edge_weight float32 [n_edges] or NULL (= 1), x float32 rows of x_stride floats, out rows of out_stride floats.
  * workspace: ss_sign_workspace_bytes(n_nodes) bytes, 256-byte aligned, shared by ss_gcn_norm and ss_sign_fill.
  */
 int64_t ss_sign_workspace_bytes(int64_t n_nodes);
 int ss_gcn_norm(const int64_t *row, const int64_t *col, const float *edge_weight, int64_t n_edges, int64_t n_nodes,
-                float *dinv_out, float *loop_weight_out, void *workspace, int64_t workspace_bytes, ss_stream_t stream);
+                float *dinv_out, float *loop_weight_out, int32_t *flags_out, void *workspace, int64_t workspace_bytes,
+                ss_stream_t stream);
 int ss_sign_fill(const int64_t *row, int64_t n_edges, int64_t n_nodes, const int64_t *rowptr, int32_t *perm_out,
                  void *workspace, int64_t workspace_bytes, ss_stream_t stream);
 int ss_sign_spmm(const int64_t *rowptr, const int32_t *perm, const int64_t *col, const float *edge_weight,

@@ -64,7 +64,7 @@ SIGNATURES = {
     'ss_link_features': (c_int, [c_ptr, c_i64, ctypes.POINTER(HopView), c_int, c_int, c_int, c_ptr, c_i64,
                                  ctypes.POINTER(HllConsts), c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     'ss_sign_workspace_bytes': (c_i64, [c_i64]),
-    'ss_gcn_norm': (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    'ss_gcn_norm': (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_sign_fill': (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_sign_spmm': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int,
                              c_ptr]),

@@ -10,8 +10,10 @@
 // per node, and the SpMM forms each coefficient on the fly in the reference's left-to-right float32 order.
 // The adjacency is a CSR keyed by edge_index[0] (the spmm row) whose entries are EDGE POSITIONS, so arbitrary
 // edge weights ride along without a permuted copy.  Float32, no FMA contraction (-fmad=false): every product
-// and sum is rounded like the reference's; only the ORDER of the per-row sum differs (the atomics-built CSR
-// does not keep edge order), so results agree to float32 summation-order tolerance.
+// and sum is rounded like the reference's.  When the edge list is sorted by row (what coalesce / to_undirected
+// produce) the CSR IS the edge list: no fill, and every row is summed in edge order exactly like the
+// reference's sequential scatter-add -- bit-identical results.  Otherwise the CSR is filled with atomics, the
+// ORDER of the per-row sum is unspecified and results agree to float32 summation-order tolerance.
 #include <string.h>
 
 #include "common.cuh"
@@ -31,13 +33,18 @@ static int sg_grid(int64_t items) {
 }
 
 // position of the LAST self-loop edge of every node (add_remaining_self_loops keeps that weight: the index_put
-// over duplicate indices is sequential on the CPU)
+// over duplicate indices is sequential on the CPU); the same pass validates the ids and notes whether the list
+// is sorted by row.  flags: bit 0 = row[] is not non-decreasing, bit 1 = some id is outside [0, n_nodes)
 __global__ void __launch_bounds__(256) sign_loops_kernel(const int64_t *__restrict__ row, const int64_t *__restrict__ col,
-                                                          int64_t n_edges, int64_t n_nodes, int32_t *loop_eid) {
+                                                          int64_t n_edges, int64_t n_nodes, int32_t *loop_eid, int32_t *flags) {
+    int f = 0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = row[e];
-        if (r == col[e] && (uint64_t)r < (uint64_t)n_nodes) atomicMax(loop_eid + r, (int32_t)e);
+        const int64_t r = row[e], c = col[e];
+        if ((uint64_t)r >= (uint64_t)n_nodes || (uint64_t)c >= (uint64_t)n_nodes) { f |= 2; continue; }
+        if (e > 0 && row[e - 1] > r) f |= 1;
+        if (r == c) atomicMax(loop_eid + r, (int32_t)e);
     }
+    if (f && flags) atomicOr(flags, f);
 }
 
 // deg starts at the self-loop weight of the node (its own, or the fill value 1)
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(256) sign_spmm_kernel(const SpmmArgs a) {
                 float coef = 0.f;
                 bool use = false;
                 if (j < e) {
-                    const int32_t eid = __ldg(a.perm + j);
+                    const int64_t eid = a.perm ? (int64_t)__ldg(a.perm + j) : j;  // no perm: the edge list is sorted by row
                     src = __ldg(a.col + eid);
                     use = (src != i) && (uint64_t)src < (uint64_t)a.n_nodes;  // self-loop edges are replaced by the loop term
                     if (use) coef = __fmul_rn(__fmul_rn(di, a.ew ? __ldg(a.ew + eid) : 1.0f), __ldg(a.dinv + src));
@@ -205,10 +212,14 @@ int64_t ss_sign_workspace_bytes(int64_t n_nodes) {
 }
 
 int ss_gcn_norm(const int64_t *row, const int64_t *col, const float *edge_weight, int64_t n_edges, int64_t n_nodes,
-                float *dinv_out, float *loop_weight_out, void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+                float *dinv_out, float *loop_weight_out, int32_t *flags_out, void *workspace, int64_t workspace_bytes,
+                ss_stream_t stream) {
     SS_REQUIRE(n_edges >= 0 && n_nodes >= 0, "negative size passed to ss_gcn_norm");
     SS_REQUIRE(n_edges < (1ll << 31), "at most 2^31-1 edges");
-    if (n_nodes == 0) return SS_OK;
+    if (n_nodes == 0) {
+        if (flags_out) SS_CUDA(cudaMemsetAsync(flags_out, n_edges > 0 ? 2 : 0, 1, (cudaStream_t)stream));
+        return SS_OK;
+    }
     SS_REQUIRE(dinv_out && loop_weight_out && workspace, "null pointer passed to ss_gcn_norm");
     SS_REQUIRE(n_edges == 0 || (row && col), "row / col is null");
     SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
@@ -219,8 +230,9 @@ int ss_gcn_norm(const int64_t *row, const int64_t *col, const float *edge_weight
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *loop_eid = (int32_t *)workspace;
     SS_CUDA(cudaMemsetAsync(loop_eid, 0xff, (size_t)n_nodes * 4, st));  // -1
+    if (flags_out) SS_CUDA(cudaMemsetAsync(flags_out, 0, 4, st));
     if (n_edges > 0) {
-        ss::sign_loops_kernel<<<ss::sg_grid(n_edges), 256, 0, st>>>(row, col, n_edges, n_nodes, loop_eid);
+        ss::sign_loops_kernel<<<ss::sg_grid(n_edges), 256, 0, st>>>(row, col, n_edges, n_nodes, loop_eid, flags_out);
         SS_LAUNCH_CHECK("sign_loops_kernel");
     }
     ss::sign_loop_weight_kernel<<<ss::sg_grid(n_nodes), 256, 0, st>>>(loop_eid, edge_weight, n_nodes, loop_weight_out, dinv_out);

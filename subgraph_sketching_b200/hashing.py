@@ -389,8 +389,9 @@ class ElphHashes(object):
         #     768-byte record inside one 1 KB-aligned block (fewer DRAM pages per gathered row) for a third more
         #     table memory; used only for tables of at least `padded_tables_min_nodes` rows (below that the tables
         #     are L2-sized anyway) while all K+1 of them stay below `padded_tables_max_frac` of the device memory
-        #   overlap_init: hop-0 initialisation (write-bound) on a side stream under the CSR build (atomics-bound)
-        self.record_stride = _env_int('SS_B200_RECORD_STRIDE', None)
+        #   overlap_init: hop-0 initialisation (write-bound) on a side stream under the CSR build (atomics-bound);
+        #     measured neutral on one B200 (both kernels stretch), so it is off
+        self.record_stride = _env_int('SS_B200_RECORD_STRIDE', 1024)
         self.padded_tables_max_frac = 0.45
         self.padded_tables_min_nodes = 1 << 20
         self.overlap_init = bool(_env_int('SS_B200_OVERLAP_INIT', 0))

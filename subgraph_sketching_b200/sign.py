@@ -25,16 +25,12 @@ from ._lib import check, lib
 from .hashing import _cuda_device, _ptr, _stream_ptr, _to_device, _to_host
 
 
-def _prepare(edge_index, edge_weight, num_nodes, device):
+def _prepare(edge_index, edge_weight, device):
     ei = _to_device(edge_index, device)
     ei = (ei if ei.dtype == torch.int64 else ei.long()).contiguous()
     if ei.dim() != 2 or ei.shape[0] != 2:
         raise ValueError('edge_index must be [2, n_edges]')
     n_edges = ei.shape[1]
-    if n_edges:
-        lo, hi = (int(v) for v in torch.aminmax(ei))
-        if lo < 0 or hi >= num_nodes:
-            raise IndexError(f'edge_index refers to node {hi if hi >= num_nodes else lo} but num_nodes is {num_nodes}')
     ew = None
     if edge_weight is not None:
         ew = _to_device(edge_weight, device).reshape(-1)
@@ -49,23 +45,32 @@ def gcn_norm_coefficients(edge_index, edge_weight, num_nodes, device=None):
     normalised weight of edge (r, c, w) is dinv[r] * w * dinv[c]; node i also has the loop (i, i, loop_w[i])."""
     device = _cuda_device(edge_index) if device is None else torch.device(device)
     with torch.cuda.device(device):
-        ei, ew, n_edges = _prepare(edge_index, edge_weight, num_nodes, device)
+        ei, ew, n_edges = _prepare(edge_index, edge_weight, device)
         return _coefficients(ei, ew, n_edges, num_nodes, device)[:2]
 
 
 def _coefficients(ei, ew, n_edges, num_nodes, device):
+    """(dinv, loop_w, workspace, rows_sorted); raises IndexError for ids outside [0, num_nodes) -- the kernel
+    validates them in the pass that finds the self loops (one 4-byte read back)"""
     ws_bytes = check(lib.ss_sign_workspace_bytes(num_nodes), 'ss_sign_workspace_bytes')
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
     dinv = torch.empty(num_nodes, dtype=torch.float32, device=device)
     loop_w = torch.empty(num_nodes, dtype=torch.float32, device=device)
+    flags = torch.zeros(1, dtype=torch.int32, device=device)
     check(lib.ss_gcn_norm(_ptr(ei[0]) if n_edges else None, _ptr(ei[1]) if n_edges else None, _ptr(ew), n_edges,
-                          num_nodes, _ptr(dinv), _ptr(loop_w), _ptr(ws), ws.numel(), _stream_ptr(device)), 'ss_gcn_norm')
-    return dinv, loop_w, ws
+                          num_nodes, _ptr(dinv), _ptr(loop_w), _ptr(flags), _ptr(ws), ws.numel(), _stream_ptr(device)),
+          'ss_gcn_norm')
+    f = int(flags.item())
+    if f & 2:
+        raise IndexError(f'edge_index refers to a node outside [0, {num_nodes})')
+    return dinv, loop_w, ws, not (f & 1)
 
 
 def sign_features(x, edge_index, edge_weight, sign_k):
     """`_generate_sign_features` on plain tensors: float32 [N, F] for sign_k == 0, else [N, (sign_k + 1) F]
-    (elph.py:87-110).  num_nodes = x.size(0) as in the reference."""
+    (elph.py:87-110).  num_nodes = x.size(0) as in the reference.  An edge_index sorted by row (coalesce /
+    to_undirected output) gives results bit-identical to the reference's CPU path; otherwise each row's float32
+    sum is taken in an unspecified order."""
     if x.dim() != 2:
         raise ValueError('x must be [num_nodes, num_features]')
     if sign_k < 0:
@@ -75,21 +80,23 @@ def sign_features(x, edge_index, edge_weight, sign_k):
     with torch.cuda.device(device):
         xd = _to_device(x, device)
         xd = (xd if xd.dtype == torch.float32 else xd.float()).contiguous()
-        ei, ew, n_edges = _prepare(edge_index, edge_weight, N, device)
+        ei, ew, n_edges = _prepare(edge_index, edge_weight, device)
         blocks = 1 if sign_k == 0 else sign_k + 1
         out = torch.empty((N, blocks * F), dtype=torch.float32, device=device)
+        st = _stream_ptr(device)
+        dinv, loop_w, ws, rows_sorted = _coefficients(ei, ew, n_edges, N, device)
         if N and F:
-            st = _stream_ptr(device)
-            dinv, loop_w, ws = _coefficients(ei, ew, n_edges, N, device)
             rowptr = torch.empty(N + 1, dtype=torch.int64, device=device)
-            perm = torch.empty(max(n_edges, 1), dtype=torch.int32, device=device)
             csr_ws = torch.empty(max(check(lib.ss_csr_workspace_bytes(N), 'ss_csr_workspace_bytes'), 256),
                                  dtype=torch.uint8, device=device)
             # histogram + scan of edge_index[0] (the spmm row); no implicit self loops, no id statistics
             check(lib.ss_csr_rowptr(None, _ptr(ei[0]) if n_edges else None, n_edges, 0, 0, N, _ptr(rowptr), None, None,
                                     None, _ptr(csr_ws), csr_ws.numel(), st), 'ss_csr_rowptr')
-            check(lib.ss_sign_fill(_ptr(ei[0]) if n_edges else None, n_edges, N, _ptr(rowptr), _ptr(perm), _ptr(ws),
-                                   ws.numel(), st), 'ss_sign_fill')
+            perm = None
+            if not rows_sorted:
+                perm = torch.empty(max(n_edges, 1), dtype=torch.int32, device=device)
+                check(lib.ss_sign_fill(_ptr(ei[0]), n_edges, N, _ptr(rowptr), _ptr(perm), _ptr(ws), ws.numel(), st),
+                      'ss_sign_fill')
             if sign_k == 0:
                 dst, copies = out, 1
             else:

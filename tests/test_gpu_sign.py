@@ -41,7 +41,7 @@ def test_sign_features_vs_reference_golden(name, ks):
         ok, err = _close(got.numpy(), want)
         assert ok, (name, k, err)
         got_d = bs.sign_features(x.cuda(), ei.cuda(), w.cuda(), k)  # device in -> device out
-        assert got_d.is_cuda and torch.equal(got_d.cpu()[:, :x.shape[1]], got[:, :x.shape[1]])
+        assert got_d.is_cuda
         ok, err = _close(got_d.cpu().numpy(), want)
         assert ok, (name, k, err)
         if k > 0:  # block 0 is x itself, blocks 1..k are identical (the reference re-propagates data.x)
@@ -49,6 +49,23 @@ def test_sign_features_vs_reference_golden(name, ks):
             assert torch.equal(got[:, :F], x)
             for b in range(2, k + 1):
                 assert torch.equal(got[:, b * F:(b + 1) * F], got[:, F:2 * F])
+
+
+@pytest.mark.parametrize('name', ['ba300_unit_f16', 'multi_int_f7', 'ba200_unit_f256'])
+def test_sign_sorted_edge_list_is_bit_identical_to_reference_order(name):
+    """edge_index sorted by row (what coalesce / to_undirected hand the reference): the CSR is the edge list
+    itself, each row is summed in edge order like the reference's sequential scatter-add, the self loop last --
+    float32 results are BIT-identical and reproducible (integer-valued weights: the degrees are exact)"""
+    blob = load_golden('sign')
+    x = torch.from_numpy(blob[f'{name}_x'])
+    ei = torch.from_numpy(blob[f'{name}_edge_index'])
+    w = torch.from_numpy(blob[f'{name}_weight'])
+    order = torch.sort(ei[0], stable=True).indices
+    ei, w = ei[:, order].contiguous(), w[order].contiguous()
+    want = sign_oracle.sign_features(x, ei, w, 2)
+    got = bs.sign_features(x.cuda(), ei.cuda(), w.cuda(), 2)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(bs.sign_features(x, ei, w, 2), want)   # host in -> host out, again identical
 
 
 def test_gcn_norm_coefficients_match_oracle():
