@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 9
+#define SS_ABI_VERSION 10
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -118,9 +118,18 @@ int ss_unpack_records(const void *rec, int64_t rec_stride, int64_t n, int num_pe
  *                   (min/max merges are order independent); reads the int32 copies when given
  * src / dst are read with coalesced loads only, so they may be PINNED HOST pointers (UVA): the edge list is
  * then consumed at PCIe rate with no staging copy, and with the int32 copies it crosses the bus once.
- * workspace: ss_csr_workspace_bytes(n_rows) bytes, 256-byte aligned, the same buffer for both calls.
+ * ss_csr_rowptr = ss_csr_degree_chunk(first = 1) over the whole list + ss_csr_rowptr_finish.  The two halves are
+ * exported for STREAMED ingestion: a host edge list is copied in chunks by the DMA engine (55 GB/s measured, against
+ * 43-48 GB/s for in-place reads by the SMs) into a small device staging ring and each chunk is histogrammed as it
+ * lands; src32_out / dst32_out then point at the chunk's slice of the int32 copies that ss_csr_fill reads.
+ * workspace: ss_csr_workspace_bytes(n_rows) bytes, 256-byte aligned, the same buffer for all calls.
  */
 int64_t ss_csr_workspace_bytes(int64_t n_rows);
+int ss_csr_degree_chunk(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t row_begin, int64_t n_rows,
+                        int32_t *src32_out, int32_t *dst32_out, int64_t *stats_io, void *workspace, int64_t workspace_bytes,
+                        int first, ss_stream_t stream);
+int ss_csr_rowptr_finish(int64_t n_self_loops, int64_t row_begin, int64_t n_rows, int64_t *rowptr, int64_t *stats_io,
+                         void *workspace, int64_t workspace_bytes, ss_stream_t stream);
 int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops,
                   int64_t row_begin, int64_t n_rows, int64_t *rowptr, int32_t *src32_out, int32_t *dst32_out,
                   int64_t *stats_out, void *workspace, int64_t workspace_bytes, ss_stream_t stream);

@@ -245,15 +245,16 @@ int64_t ss_csr_workspace_bytes(int64_t n_rows) {
     return ss::workspace_bytes(n_rows);
 }
 
-int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
-                  int64_t n_rows, int64_t *rowptr, int32_t *src32_out, int32_t *dst32_out, int64_t *stats_out,
-                  void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
-    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_rowptr");
-    SS_REQUIRE(rowptr && workspace, "null pointer passed to ss_csr_rowptr");
+// pass 1 over ONE CHUNK of the COO list: accumulates the in-degree histogram and the id statistics, writes the
+// int32 copies of the chunk.  `first` zeroes the histogram and initialises the statistics.
+int ss_csr_degree_chunk(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t row_begin, int64_t n_rows,
+                        int32_t *src32_out, int32_t *dst32_out, int64_t *stats_io, void *workspace, int64_t workspace_bytes,
+                        int first, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_degree_chunk");
+    SS_REQUIRE(workspace, "null workspace passed to ss_csr_degree_chunk");
     SS_REQUIRE(n_edges == 0 || dst, "dst is null");
-    SS_REQUIRE(n_self_loops >= 0 || stats_out, "n_self_loops < 0 (= max id + 1) needs stats_out");
-    SS_REQUIRE(!stats_out || n_edges == 0 || src, "src is required for the id statistics");
-    SS_REQUIRE(!(src32_out || dst32_out) || stats_out, "32-bit copies are written together with the statistics");
+    SS_REQUIRE(!stats_io || n_edges == 0 || src, "src is required for the id statistics");
+    SS_REQUIRE(!(src32_out || dst32_out) || stats_io, "32-bit copies are written together with the statistics");
     SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     if (workspace_bytes < ss::workspace_bytes(n_rows)) {
         ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes,
@@ -261,17 +262,15 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
         return SS_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    long long *stats = (long long *)stats_out;
-    if (stats) {
-        const long long init[4] = {-1, 0, 0, 0x7fffffffffffffffll};
-        SS_CUDA(cudaMemcpyAsync(stats, init, sizeof(init), cudaMemcpyHostToDevice, st));  // staged before returning
-    }
-    if (n_rows == 0 && !stats) {
-        SS_CUDA(cudaMemsetAsync(rowptr, 0, 8, st));
-        return SS_OK;
-    }
+    long long *stats = (long long *)stats_io;
     ss::CsrWorkspace w = ss::carve(workspace, n_rows);
-    if (n_rows > 0) SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
+    if (first) {
+        if (stats) {
+            const long long init[4] = {-1, 0, 0, 0x7fffffffffffffffll};
+            SS_CUDA(cudaMemcpyAsync(stats, init, sizeof(init), cudaMemcpyHostToDevice, st));  // staged before returning
+        }
+        if (n_rows > 0) SS_CUDA(cudaMemsetAsync(w.deg, 0, (size_t)n_rows * 4, st));
+    }
     if (n_edges > 0) {
         int64_t blocks = (n_edges + 255) / 256;
         int64_t cap = (int64_t)ss::sm_count() * 32;
@@ -279,10 +278,28 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
                                                                          src32_out, dst32_out, stats);
         SS_LAUNCH_CHECK("degree_kernel");
     }
+    return SS_OK;
+}
+
+// exclusive scan of the accumulated in-degrees (+ implicit self loops) -> rowptr; completes stats[1..2]
+int ss_csr_rowptr_finish(int64_t n_self_loops, int64_t row_begin, int64_t n_rows, int64_t *rowptr, int64_t *stats_io,
+                         void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+    SS_REQUIRE(n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_rowptr_finish");
+    SS_REQUIRE(rowptr && workspace, "null pointer passed to ss_csr_rowptr_finish");
+    SS_REQUIRE(n_self_loops >= 0 || stats_io, "n_self_loops < 0 (= max id + 1) needs the statistics");
+    SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    if (workspace_bytes < ss::workspace_bytes(n_rows)) {
+        ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes,
+                      (long long)ss::workspace_bytes(n_rows));
+        return SS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    long long *stats = (long long *)stats_io;
     if (n_rows == 0) {
         SS_CUDA(cudaMemsetAsync(rowptr, 0, 8, st));
         return SS_OK;
     }
+    ss::CsrWorkspace w = ss::carve(workspace, n_rows);
     ss::tile_sum_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, row_begin, n_self_loops, stats, w.tile_sum);
     SS_LAUNCH_CHECK("tile_sum_kernel");
     ss::tile_scan_kernel<<<1, 1024, 0, st>>>(w.tile_sum, w.n_tiles);
@@ -291,6 +308,17 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
                                                                 rowptr);
     SS_LAUNCH_CHECK("rowptr_kernel");
     return SS_OK;
+}
+
+int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_self_loops, int64_t row_begin,
+                  int64_t n_rows, int64_t *rowptr, int32_t *src32_out, int32_t *dst32_out, int64_t *stats_out,
+                  void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+    SS_REQUIRE(rowptr, "null pointer passed to ss_csr_rowptr");
+    SS_REQUIRE(n_self_loops >= 0 || stats_out, "n_self_loops < 0 (= max id + 1) needs stats_out");
+    int rc = ss_csr_degree_chunk(src, dst, n_edges, row_begin, n_rows, src32_out, dst32_out, stats_out, workspace,
+                                 workspace_bytes, 1, stream);
+    if (rc != SS_OK) return rc;
+    return ss_csr_rowptr_finish(n_self_loops, row_begin, n_rows, rowptr, stats_out, workspace, workspace_bytes, stream);
 }
 
 int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,

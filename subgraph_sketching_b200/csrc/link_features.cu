@@ -250,8 +250,20 @@ __global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a)
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // the endpoints of the NEXT link are fetched while the current one is evaluated: the id load (a dependent
+    // round trip in front of every record load -- over PCIe when the link list is a pinned host buffer) leaves the
+    // critical path
+    int64_t u_next = 0, v_next = 0;
+    if (gwarp < a.n_links) {
+        u_next = __ldg(a.links + 2 * gwarp);
+        v_next = __ldg(a.links + 2 * gwarp + 1);
+    }
     for (int64_t i = gwarp; i < a.n_links; i += n_warps) {
-        const int64_t u = checked_node(a, __ldg(a.links + 2 * i)), v = checked_node(a, __ldg(a.links + 2 * i + 1));
+        const int64_t u = checked_node(a, u_next), v = checked_node(a, v_next);
+        if (i + n_warps < a.n_links) {
+            u_next = __ldg(a.links + 2 * (i + n_warps));
+            v_next = __ldg(a.links + 2 * (i + n_warps) + 1);
+        }
         uint4 mu[K], mv[K];
         uint2 hu[K], hv[K];
 #pragma unroll

@@ -179,11 +179,55 @@ def _edge_source(edge_index, device):
     return ei.contiguous(), False
 
 
+# a pinned host edge list of at least this many edges is STREAMED: DMA copies of INGEST_CHUNK edges into a
+# two-slot device staging ring, each chunk histogrammed as it lands (copy engine 55.6 GB/s, against 42-48 GB/s
+# for in-place reads of the same list by the SMs -- tools/exp_h2d.py)
+INGEST_MIN_EDGES = 1 << 23
+INGEST_CHUNK = 1 << 25
+_ingest_streams = {}
+
+
+def _ingest_stream(device):
+    key = str(device)
+    if key not in _ingest_streams:
+        _ingest_streams[key] = torch.cuda.Stream(device=device)
+    return _ingest_streams[key]
+
+
+def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device):
+    """pass 1 of the CSR build over a pinned host edge_index [2, E]: chunked DMA into a staging ring on the
+    ingest stream, ss_csr_degree_chunk per chunk on the current stream"""
+    main = torch.cuda.current_stream(device)
+    copy = _ingest_stream(device)
+    chunk = min(INGEST_CHUNK, n_edges)
+    ring = [torch.empty((2, chunk), dtype=torch.int64, device=device) for _ in range(2)]
+    copy.wait_stream(main)  # the ring's memory may still be in use by earlier work on this stream
+    consumed = [None, None]
+    for c, lo in enumerate(range(0, n_edges, chunk)):
+        hi = min(lo + chunk, n_edges)
+        buf = ring[c & 1]
+        with torch.cuda.stream(copy):
+            if consumed[c & 1] is not None:
+                copy.wait_event(consumed[c & 1])
+            buf[0, :hi - lo].copy_(ei[0, lo:hi], non_blocking=True)  # contiguous row slices: plain DMA copies
+            buf[1, :hi - lo].copy_(ei[1, lo:hi], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        main.wait_event(ready)
+        check(lib.ss_csr_degree_chunk(_ptr(buf[0]), _ptr(buf[1]), hi - lo, row_begin, num_rows, _ptr(src32[lo:hi]),
+                                      _ptr(dst32[lo:hi]), _ptr(stats), _ptr(ws), ws.numel(), 1 if c == 0 else 0,
+                                      _stream_ptr(device)), 'ss_csr_degree_chunk')
+        consumed[c & 1] = torch.cuda.Event()
+        consumed[c & 1].record(main)
+    return ring  # kept alive by the caller until the current stream has consumed it
+
+
 def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bounds_fn=None):
     """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [nnz], nnz, max_id) keyed by destination
     (PyG flow source -> target, hashing.py:30-35).  With add_loops, a self loop is appended for every node id
     < max(edge_index)+1 (computed on the device), which is add_self_loops(edge_index) without num_nodes
-    (hashing.py:148).  One device->host read (32 bytes of statistics) sizes colidx."""
+    (hashing.py:148).  One device->host read (32 bytes of statistics) sizes colidx.  A pinned host edge_index
+    never gets a full-size device copy: it is streamed through a staging ring (large lists) or read in place."""
     ei, zero_copy = _edge_source(edge_index, device)
     n_edges = ei.shape[1]
     if num_rows is None:  # rows = max id + 1: needs the id statistics first
@@ -199,9 +243,16 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
         dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
     st = _stream_ptr(device)
     loops = -1 if add_loops else 0
-    check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, loops, row_begin, num_rows, _ptr(rowptr), _ptr(src32),
-                            _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
+    ring = None
+    if zero_copy and n_edges >= INGEST_MIN_EDGES:
+        ring = _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device)
+        check(lib.ss_csr_rowptr_finish(loops, row_begin, num_rows, _ptr(rowptr), _ptr(stats), _ptr(ws), ws.numel(), st),
+              'ss_csr_rowptr_finish')
+    else:
+        check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, loops, row_begin, num_rows, _ptr(rowptr), _ptr(src32),
+                                _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
     max_id, nnz, _, min_id = (int(v) for v in stats.tolist())
+    del ring
     if n_edges and min_id < 0:
         raise IndexError(f'edge_index holds a negative node id ({min_id})')
     if max_id >= (1 << 31):
@@ -723,9 +774,9 @@ class ElphHashes(object):
             batch_size = max(int(batch_size), 1)
             main = torch.cuda.current_stream(device)
 
-            def launch(lo, hi, out_rows):
+            def launch(link_rows, out_rows):
                 ev = self._event_begin(device)
-                check(lib.ss_link_features(_ptr(ld[lo:hi]), hi - lo, views, K, self.num_perm, self.p, _ptr(cd),
+                check(lib.ss_link_features(_ptr(link_rows), link_rows.shape[0], views, K, self.num_perm, self.p, _ptr(cd),
                                            cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out_rows), None, _ptr(err),
                                            _stream_ptr(device)), 'ss_link_features')
                 self._event_end('link_features', ev, device)
@@ -734,11 +785,15 @@ class ElphHashes(object):
                 out = torch.empty((n, F), dtype=torch.float32, device=device)
                 for lo in range(0, n, batch_size):
                     hi = min(lo + batch_size, n)
-                    launch(lo, hi, out[lo:hi])
+                    launch(ld[lo:hi], out[lo:hi])
                 self._raise_if_flagged(err, views)
                 return out
-            # host result: kernels on the current stream, device->pinned-host copies of finished batches on a
-            # side stream, double buffered -- the copy of batch b overlaps the kernel of batch b + 1
+            # host result: a three-stage pipeline over batches of `step` links, double buffered --
+            #   ingest stream : DMA of the next batch of a pinned link list into a device slot (a pageable list was
+            #                   copied to the device as a whole above)
+            #   current stream: the kernel
+            #   side stream   : device -> pinned-host copy of the finished batch
+            # so the H2D copy of batch b + 1 and the D2H copy of batch b - 1 overlap the kernel of batch b
             try:
                 out = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
             except RuntimeError:
@@ -747,14 +802,42 @@ class ElphHashes(object):
             side = self._side_stream(device)
             bufs = [torch.empty((min(step, max(n, 1)), F), dtype=torch.float32, device=device) for _ in range(2)]
             freed = [None, None]
+            staged = not ld.is_cuda  # pinned host list
+            if staged:
+                ingest = _ingest_stream(device)
+                lbufs = [torch.empty((min(step, max(n, 1)), 2), dtype=torch.int64, device=device) for _ in range(2)]
+                ingest.wait_stream(main)
+                kernel_done = [None, None]
+
+                def stage_in(b):
+                    lo_ = b * step
+                    hi_ = min(lo_ + step, n)
+                    with torch.cuda.stream(ingest):
+                        if kernel_done[b & 1] is not None:
+                            ingest.wait_event(kernel_done[b & 1])
+                        lbufs[b & 1][:hi_ - lo_].copy_(ld[lo_:hi_], non_blocking=True)
+                        ev_in = torch.cuda.Event()
+                        ev_in.record(ingest)
+                    return ev_in
+
+                n_batches = (n + step - 1) // step
+                arrived = stage_in(0) if n_batches else None
             for b, lo in enumerate(range(0, n, step)):
                 hi = min(lo + step, n)
                 buf = bufs[b & 1][:hi - lo]
                 if freed[b & 1] is not None:
                     main.wait_event(freed[b & 1])
-                launch(lo, hi, buf)
+                if staged:
+                    main.wait_event(arrived)
+                    launch(lbufs[b & 1][:hi - lo], buf)
+                else:
+                    launch(ld[lo:hi], buf)
                 done = torch.cuda.Event()
                 done.record(main)
+                if staged:
+                    kernel_done[b & 1] = done
+                    if b + 1 < n_batches:
+                        arrived = stage_in(b + 1)
                 with torch.cuda.stream(side):
                     side.wait_event(done)
                     out[lo:hi].copy_(buf, non_blocking=True)

@@ -444,7 +444,7 @@ def test_link_feature_front_ends_agree(monkeypatch):
             assert all(torch.equal(ia[k], ib[k]) for k in ia)
 
 
-def test_pinned_host_inputs_are_read_in_place():
+def test_pinned_host_inputs_are_read_in_place(monkeypatch):
     """BUDDY-style CPU inputs: a pinned edge_index / link list is consumed by the kernels over PCIe without a
     staging copy; results equal the device-resident path bit for bit, out-of-range ids still raise"""
     n, K = 6000, 2
@@ -468,6 +468,18 @@ def test_pinned_host_inputs_are_read_in_place():
         c_ref = c_dev.clone()
         c_ref[0, 0] += 1.0
         assert torch.equal(f_mod, eh.get_subgraph_features(links[:16].to(DEV), t_dev, c_ref).cpu())
+    # large pinned lists are streamed (chunked DMA into a staging ring, one degree pass per chunk): force that
+    # path with a tiny chunk so that the ring wraps many times and ends on a ragged chunk
+    from subgraph_sketching_b200 import hashing as hmod
+    monkeypatch.setattr(hmod, 'INGEST_MIN_EDGES', 1)
+    monkeypatch.setattr(hmod, 'INGEST_CHUNK', 7001)
+    t_s, c_s = eh.build_hash_tables(n, ei.pin_memory())
+    assert torch.equal(c_s, c_dev.cpu())
+    for k in range(K + 1):
+        assert torch.equal(t_s.records(k), t_dev.records(k))
+    with pytest.raises(IndexError):
+        eh.build_hash_tables(n, torch.tensor([[0, -1], [1, 2]]).pin_memory())
+    monkeypatch.undo()
     bad = links.clone()
     bad[5, 1] = n
     with pytest.raises(IndexError):
