@@ -440,12 +440,13 @@ class ElphHashes(object):
         #     768-byte record inside one 1 KB-aligned block (fewer DRAM pages per gathered row) for a third more
         #     table memory; used only for tables of at least `padded_tables_min_nodes` rows (below that the tables
         #     are L2-sized anyway) while all K+1 of them stay below `padded_tables_max_frac` of the device memory
-        #   overlap_init: hop-0 initialisation (write-bound) on a side stream under the CSR build (atomics-bound);
-        #     measured neutral on one B200 (both kernels stretch), so it is off
+        #   overlap_init: hop-0 initialisation (write-bound) on a side stream under the CSR build.  None = auto:
+        #     only when the edge list is streamed from pinned host memory (the SMs idle behind the DMA engine, the
+        #     3.8 ms are free); against a device-resident list it is neutral (both kernels stretch), so off there
         self.record_stride = _env_int('SS_B200_RECORD_STRIDE', 1024)
         self.padded_tables_max_frac = 0.45
         self.padded_tables_min_nodes = 1 << 20
-        self.overlap_init = bool(_env_int('SS_B200_OVERLAP_INIT', 0))
+        self.overlap_init = {None: None, 0: False}.get(_env_int('SS_B200_OVERLAP_INIT', None), True)
         # linear-counting table, evaluated with the reference's own float32 torch expression (hashing.py:195)
         nz = torch.arange(1, self.m + 1, dtype=torch.int64)
         self._lc_host = torch.cat([torch.zeros(1), self.m * torch.log(self.m / nz)]).float()
@@ -632,7 +633,11 @@ class ElphHashes(object):
             recs = self._alloc_hop_tables(num_nodes, rb, device)
             main = torch.cuda.current_stream(device)
             init_done = None
-            if self.overlap_init and num_nodes > 0:
+            overlap = self.overlap_init
+            if overlap is None:
+                overlap = (edge_index.device.type == 'cpu' and edge_index.dim() == 2 and edge_index.is_pinned()
+                           and edge_index.shape[1] >= INGEST_MIN_EDGES)
+            if overlap and num_nodes > 0:
                 # hop 0 does not depend on the graph: enqueue it first, on the side stream, so that it runs under
                 # the CSR build (which also holds the only host synchronisation of this function)
                 side = self._side_stream(device)
