@@ -16,10 +16,12 @@
 // ranges) and lets the row pipeline run across row boundaries on low-degree graphs.  min/max are
 // idempotent and commutative, so any split / order is bit-exact.
 //
-// Two streaming engines, same decomposition:
-//   TMA: lanes issue one `cp.async.bulk` (SASS UBLKCP) per neighbour row into a per-warp shared-memory ring;
-//        completion is tracked with one mbarrier per stage; the warp then reads the rows conflict-free.
-//   LDG: each lane issues LDG.128 + LDG.64 per neighbour row, U rows in flight in registers.
+// Streaming engines, same decomposition:
+//   TMA : lane 0 issues ONE `cp.async.bulk.tensor.2d ... tile::gather4` (SASS UTMALDG.2D.GATHER4) per group of 4
+//         neighbour rows into a per-warp shared-memory ring; completion is tracked with one mbarrier per stage;
+//         the warp then reads the rows conflict-free.  The default.
+//   BULK: same ring, four 1-D `cp.async.bulk` copies (SASS UBLKCP) per group.
+//   LDG : each lane issues LDG.128 + LDG.64 per neighbour row, U rows in flight in registers.
 // The generic kernel (any P, p) is row-per-warp with a column-chunk outer loop.
 #include <stdlib.h>
 #include <string.h>
