@@ -311,6 +311,11 @@ def main():
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak if achieved else None,
                 'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': merge_bytes,
                 'avg_launch_ms': merge_ms, 'launches_timed': len(stage_ms.get('khop_merge', []))}
+    if traffic and merge_ms and not distributed:
+        # the same launch time against the DRAM bytes ncu measured for this kernel and workload: `frac` above can
+        # exceed 1 because the algorithmic model counts every neighbour record once per edge while hub records hit in L2
+        roofline['dram_achieved'] = traffic / (merge_ms * 1e-3) / 1e9
+        roofline['dram_frac'] = roofline['dram_achieved'] / peak
     L_local = (link_slice(L, world, rank)[1] - link_slice(L, world, rank)[0]) if distributed else L
     link_bytes = L_local * (2 * K * R + 16 + 8 * K + 4 * F)
     lf_ms = sum(stage_ms.get('link_features', [])) / a.steps if stage_ms.get('link_features') else None
