@@ -44,6 +44,32 @@ def test_record_geometry_and_argument_errors():
     assert _lib.lib.ss_merge_workspace_bytes(10, 33, 6) == 16
 
 
+def test_argument_validation_needs_no_gpu():
+    """every entry point validates sizes / pointers before it touches CUDA: bad arguments come back as
+    SS_ERR_INVALID (-1) with a message, on a machine without a GPU too"""
+    lib = _lib.lib
+    assert lib.ss_sign_workspace_bytes(1000) >= 8000 and lib.ss_sign_workspace_bytes(-1) < 0
+    assert lib.ss_gcn_norm(None, None, None, -1, 10, None, None, None, None, 0, None) == -1
+    assert b'negative' in lib.ss_last_error()
+    assert lib.ss_gcn_norm(None, None, None, 1 << 31, 10, None, None, None, None, 0, None) == -1
+    assert b'2^31' in lib.ss_last_error()
+    assert lib.ss_gcn_norm(None, None, None, 5, 10, None, None, None, None, 0, None) == -1      # null outputs
+    assert lib.ss_sign_fill(None, 5, 10, None, None, None, 0, None) == -1
+    assert lib.ss_sign_spmm(None, None, None, None, None, None, None, 4, 10, 8, None, 8, 1, None) == -1
+    assert lib.ss_sign_spmm(None, None, None, None, None, None, None, 8, 10, 8, None, 8, 0, None) == -1  # copies < 1
+    assert lib.ss_sign_spmm(None, None, None, None, None, None, None, 8, 0, 8, None, 8, 1, None) == 0   # empty: no-op
+    assert lib.ss_csr_degree_chunk(None, None, -1, 0, 10, None, None, None, None, 0, 1, None) == -1
+    assert lib.ss_csr_degree_chunk(None, None, 4, 0, 10, None, None, None, None, 0, 1, None) == -1      # null workspace
+    assert lib.ss_csr_rowptr_finish(-1, 0, 10, None, None, None, 0, None) == -1
+    assert lib.ss_csr_rowptr(None, None, 0, 0, 0, 10, None, None, None, None, None, 0, None) == -1
+    assert lib.ss_khop_merge(None, None, 5, 0, None, 5, 768, None, 768, 128, 3, None, 0, None, 0, None, 0, None) == -1
+    assert b'unsupported sketch shape' in lib.ss_last_error()
+    assert lib.ss_link_features(None, 5, None, 4, 128, 8, None, 0, None, 0, None, None, None, None) == -1
+    assert b'1, 2 and 3 hop' in lib.ss_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(lib.ss_sign_fill(None, -3, 10, None, None, None, 0, None), 'ss_sign_fill')
+
+
 def test_constructor_mirrors_reference():
     for bad in (0, 4):
         with pytest.raises(AssertionError):
