@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 10
+#define SS_ABI_VERSION 11
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -136,6 +136,15 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
 int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,
                 int64_t n_self_loops, const int64_t *stats, int64_t row_begin, int64_t n_rows, const int64_t *rowptr,
                 int32_t *colidx, void *workspace, int64_t workspace_bytes, ss_stream_t stream);
+/* EXPERIMENTAL, opt-in (SS_B200_CSR_BIN=1 in the Python host), not on the default path: one streaming pass that groups
+ * the edges by destination block (dst >> shift, at most 2048 blocks; capacities = differences of rowptr) into
+ * src32_out / dst32_out so that the fill walks colidx window by window and completes its 32-byte sectors in L2.
+ * Writes rowptr[n_rows] - (self loops in range) entries; then call ss_csr_fill with src32 = src32_out,
+ * dst32 = dst32_out and that count as n_edges.  workspace: ss_csr_bin_workspace_bytes() bytes, zeroed by the caller. */
+int64_t ss_csr_bin_workspace_bytes(void);
+int ss_csr_bin_edges(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,
+                     int64_t n_self_loops, const int64_t *stats, int64_t row_begin, int64_t n_rows, const int64_t *rowptr,
+                     int32_t *src32_out, int32_t *dst32_out, void *workspace, int64_t workspace_bytes, ss_stream_t stream);
 
 /* ---- K2: one hop of sketch propagation ----------------------------------------------------------
  * Replaces MinhashPropagation.forward + HllPropagation.forward (hashing.py:28-45, called at :160-162)

@@ -230,6 +230,83 @@ __global__ void __launch_bounds__(256) fill_kernel(const IdT *__restrict__ src, 
     }
 }
 
+// ---- EXPERIMENTAL (opt-in, not on the default path; unmeasured): coarse binning of the edge list by destination
+// block before the fill.  The fill's cost is its scattered 4-byte stores: an edge list sorted by source hits a
+// random row of the 2 GB colidx array per edge, so every 32-byte sector is written ~8 times at unrelated moments
+// and travels to DRAM half empty each time.  One extra streaming pass that groups the edges by dst >> shift
+// (<= 2048 buckets) makes the fill walk colidx window by window (1-2 MB at a time, L2 resident), so sectors are
+// completed in L2.  The bucket capacities are free: they are differences of the rowptr the scan just produced.
+constexpr int BIN_MAX_BUCKETS = 2048;
+constexpr int BIN_EPT = 32;                       // edges per thread per tile
+constexpr int BIN_TILE = 256 * BIN_EPT;
+
+static int bin_shift_for(int64_t n_rows) {
+    int s = 0;
+    while (((n_rows + ((int64_t)1 << s) - 1) >> s) > BIN_MAX_BUCKETS) ++s;
+    return s;
+}
+
+// edges (self loops excluded) whose local destination row is < r
+__device__ __forceinline__ int64_t edge_prefix(const int64_t *__restrict__ rowptr, int64_t r, int64_t row_begin,
+                                               int64_t n_self_loops) {
+    int64_t loops = n_self_loops - row_begin;
+    loops = loops < 0 ? 0 : (loops > r ? r : loops);
+    return rowptr[r] - loops;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(256) bin_edges_kernel(const IdT *__restrict__ src, const IdT *__restrict__ dst,
+                                                         int64_t n_edges, int64_t n_self_loops_arg, const long long *stats,
+                                                         int64_t row_begin, int64_t n_rows, int shift, int n_buckets,
+                                                         const int64_t *__restrict__ rowptr, unsigned long long *cursors,
+                                                         int32_t *__restrict__ src_out, int32_t *__restrict__ dst_out) {
+    __shared__ uint32_t count[BIN_MAX_BUCKETS];          // entries of this tile per bucket, then the running offset
+    __shared__ unsigned long long base[BIN_MAX_BUCKETS]; // where this tile's run starts in each bucket
+    const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
+    const int64_t n_tiles = (n_edges + BIN_TILE - 1) / BIN_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int b = threadIdx.x; b < n_buckets; b += blockDim.x) count[b] = 0u;
+        __syncthreads();
+        int32_t s32[BIN_EPT], d32[BIN_EPT];  // d32 = -1 marks an edge that is not binned
+        const int64_t e0 = tile * BIN_TILE + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < BIN_EPT; ++i) {
+            const int64_t e = e0 + (int64_t)i * 256;
+            d32[i] = -1;
+            s32[i] = 0;
+            if (e < n_edges) {
+                const int64_t dv = (int64_t)dst[e];
+                const int64_t d = dv - row_begin;
+                if (d >= 0 && d < n_rows) {
+                    d32[i] = (int32_t)dv;
+                    s32[i] = (int32_t)src[e];
+                    atomicAdd(&count[(int)(d >> shift)], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < n_buckets; b += blockDim.x) {
+            const uint32_t c = count[b];
+            if (c) {
+                const unsigned long long start = (unsigned long long)edge_prefix(rowptr, (int64_t)b << shift, row_begin, n_self_loops);
+                base[b] = start + atomicAdd(cursors + b, (unsigned long long)c);
+                count[b] = 0u;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < BIN_EPT; ++i) {
+            if (d32[i] >= 0) {
+                const int b = (int)(((int64_t)d32[i] - row_begin) >> shift);
+                const unsigned long long pos = base[b] + atomicAdd(&count[b], 1u);
+                src_out[pos] = s32[i];
+                dst_out[pos] = d32[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // SS_B200_CSR_FILL=legacy keeps zero-based cursors + a rowptr read per edge (the first version)
 static bool abs_cursor_fill() {
     const char *e = getenv("SS_B200_CSR_FILL");
@@ -319,6 +396,41 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
                                  workspace_bytes, 1, stream);
     if (rc != SS_OK) return rc;
     return ss_csr_rowptr_finish(n_self_loops, row_begin, n_rows, rowptr, stats_out, workspace, workspace_bytes, stream);
+}
+
+// EXPERIMENTAL (see bin_edges_kernel): groups the edges whose destination lies in [row_begin, row_begin + n_rows)
+// by destination block into src32_out / dst32_out (int32, rowptr[n_rows] - self loops entries), ready for
+// ss_csr_fill(src32 = src32_out, dst32 = dst32_out, n_edges = that count).  workspace: ss_csr_bin_workspace_bytes()
+// bytes, ZEROED by the caller.
+int64_t ss_csr_bin_workspace_bytes(void) { return (int64_t)ss::BIN_MAX_BUCKETS * 8; }
+
+int ss_csr_bin_edges(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,
+                     int64_t n_self_loops, const int64_t *stats, int64_t row_begin, int64_t n_rows, const int64_t *rowptr,
+                     int32_t *src32_out, int32_t *dst32_out, void *workspace, int64_t workspace_bytes, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_bin_edges");
+    if (n_edges == 0 || n_rows == 0) return SS_OK;
+    SS_REQUIRE(rowptr && workspace && src32_out && dst32_out, "null pointer passed to ss_csr_bin_edges");
+    SS_REQUIRE((src && dst) || (src32 && dst32), "src/dst is null");
+    SS_REQUIRE(n_self_loops >= 0 || stats, "n_self_loops < 0 (= max id + 1) needs the statistics of ss_csr_rowptr");
+    SS_REQUIRE(src32_out != src32 && dst32_out != dst32, "binning is not in place");
+    SS_REQUIRE(((uintptr_t)workspace & 7) == 0 && workspace_bytes >= ss_csr_bin_workspace_bytes(),
+               "bin workspace must be 8-byte aligned and ss_csr_bin_workspace_bytes() long");
+    const int shift = ss::bin_shift_for(n_rows);
+    const int n_buckets = (int)((n_rows + ((int64_t)1 << shift) - 1) >> shift);
+    int64_t tiles = (n_edges + ss::BIN_TILE - 1) / ss::BIN_TILE;
+    int64_t cap = (int64_t)ss::sm_count() * 4;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long *stp = (const long long *)stats;
+    unsigned long long *cur = (unsigned long long *)workspace;
+    if (src32 && dst32)
+        ss::bin_edges_kernel<int32_t><<<grid, 256, 0, st>>>(src32, dst32, n_edges, n_self_loops, stp, row_begin, n_rows, shift,
+                                                            n_buckets, rowptr, cur, src32_out, dst32_out);
+    else
+        ss::bin_edges_kernel<int64_t><<<grid, 256, 0, st>>>(src, dst, n_edges, n_self_loops, stp, row_begin, n_rows, shift,
+                                                            n_buckets, rowptr, cur, src32_out, dst32_out);
+    SS_LAUNCH_CHECK("bin_edges_kernel");
+    return SS_OK;
 }
 
 int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,

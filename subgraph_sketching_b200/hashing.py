@@ -251,13 +251,27 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
     else:
         check(lib.ss_csr_rowptr(_ptr(src), _ptr(dst), n_edges, loops, row_begin, num_rows, _ptr(rowptr), _ptr(src32),
                                 _ptr(dst32), _ptr(stats), _ptr(ws), ws.numel(), st), 'ss_csr_rowptr')
-    max_id, nnz, _, min_id = (int(v) for v in stats.tolist())
+    max_id, nnz, n_loops_used, min_id = (int(v) for v in stats.tolist())
     del ring
     if n_edges and min_id < 0:
         raise IndexError(f'edge_index holds a negative node id ({min_id})')
     if max_id >= (1 << 31):
         raise IndexError('node ids must be < 2^31')
     colidx = torch.empty(max(nnz, 4), dtype=torch.int32, device=device)
+    if _env_int('SS_B200_CSR_BIN', 0) and n_edges >= _env_int('SS_B200_CSR_BIN_MIN_EDGES', 1 << 22):
+        # EXPERIMENTAL, opt-in, unmeasured: group the edges by destination block first so that the fill's scattered
+        # stores stay inside an L2-resident window of colidx (csrc/csr.cu: bin_edges_kernel)
+        n_binned = nnz - min(max(n_loops_used - row_begin, 0), num_rows)
+        b_src = torch.empty(max(n_binned, 1), dtype=torch.int32, device=device)
+        b_dst = torch.empty(max(n_binned, 1), dtype=torch.int32, device=device)
+        bws = torch.zeros(check(lib.ss_csr_bin_workspace_bytes(), 'ss_csr_bin_workspace_bytes'), dtype=torch.uint8,
+                          device=device)
+        check(lib.ss_csr_bin_edges(_ptr(src), _ptr(dst), _ptr(src32), _ptr(dst32), n_edges, loops, _ptr(stats), row_begin,
+                                   num_rows, _ptr(rowptr), _ptr(b_src), _ptr(b_dst), _ptr(bws), bws.numel(), st),
+              'ss_csr_bin_edges')
+        check(lib.ss_csr_fill(None, None, _ptr(b_src), _ptr(b_dst), n_binned, loops, _ptr(stats), row_begin, num_rows,
+                              _ptr(rowptr), _ptr(colidx), _ptr(ws), ws.numel(), st), 'ss_csr_fill')
+        return rowptr, colidx, nnz, max_id
     check(lib.ss_csr_fill(_ptr(src), _ptr(dst), _ptr(src32), _ptr(dst32), n_edges, loops, _ptr(stats), row_begin,
                           num_rows, _ptr(rowptr), _ptr(colidx), _ptr(ws), ws.numel(), st), 'ss_csr_fill')
     return rowptr, colidx, nnz, max_id

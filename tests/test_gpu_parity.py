@@ -602,3 +602,39 @@ def test_layout_and_scheduling_knobs_are_bit_equal(monkeypatch):
     with pytest.raises(ValueError):
         eh.record_stride = 1000
         eh.build_hash_tables(n, ei)
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('SS_TEST_EXPERIMENTAL'),
+                    reason='opt-in: experimental, not yet measured paths (set SS_TEST_EXPERIMENTAL=1)')
+def test_experimental_binned_csr_fill_is_equivalent(monkeypatch):
+    """SS_B200_CSR_BIN=1 (edges grouped by destination block before the fill) must give the same adjacency: equal
+    rowptr, equal neighbour multiset per row, bit-equal tables -- device and pinned-host inputs, row ranges"""
+    n = 1 << 15
+    dev = torch.device(DEV)
+    ei = rmat_edges(15, 16, 6, dev)
+    ref = ssb.build_csr(ei, dev, num_rows=n, add_loops=True)
+    monkeypatch.setenv('SS_B200_CSR_BIN', '1')
+    monkeypatch.setenv('SS_B200_CSR_BIN_MIN_EDGES', '1')
+    for inp in (ei, ei.cpu().pin_memory()):
+        got = ssb.build_csr(inp, dev, num_rows=n, add_loops=True)
+        assert torch.equal(got[0], ref[0]) and got[2] == ref[2] and got[3] == ref[3]
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), ref[0][1:] - ref[0][:-1])
+        key_ref = torch.sort(rows * n + ref[1][:ref[2]].long()).values
+        key_got = torch.sort(rows * n + got[1][:got[2]].long()).values
+        assert torch.equal(key_ref, key_got)
+    lo, hi = 1000, 9000  # a row range, as the node-sharded engine builds it
+    part = ssb.build_csr(ei, dev, num_rows=hi - lo, add_loops=True, row_begin=lo)
+    monkeypatch.delenv('SS_B200_CSR_BIN')
+    want = ssb.build_csr(ei, dev, num_rows=hi - lo, add_loops=True, row_begin=lo)
+    assert torch.equal(part[0], want[0]) and part[2] == want[2]
+    rows = torch.repeat_interleave(torch.arange(hi - lo, device=dev), want[0][1:] - want[0][:-1])
+    assert torch.equal(torch.sort(rows * n + part[1][:part[2]].long()).values,
+                       torch.sort(rows * n + want[1][:want[2]].long()).values)
+    monkeypatch.setenv('SS_B200_CSR_BIN', '1')
+    eh = ssb.ElphHashes(make_args(2))
+    t1, c1 = eh.build_hash_tables(n, ei)
+    monkeypatch.delenv('SS_B200_CSR_BIN')
+    t0, c0 = eh.build_hash_tables(n, ei)
+    for k in range(3):
+        assert torch.equal(t1.records(k), t0.records(k))
+    assert torch.equal(c1, c0)

@@ -2,8 +2,8 @@
 
     python tools/exp_knobs.py [scale] [links]        -> gpurun_out/exp_knobs.json (+ stdout table)
 
-Configurations: CSR fill with zero-based cursors + rowptr read per edge (legacy) vs absolute cursors; hop-0
-initialisation on a side stream under the CSR build; 1024-byte record stride.  Every configuration is checked
+Configurations: CSR fill with zero-based cursors + rowptr read per edge (legacy) vs absolute cursors; 1024-byte
+record stride; the experimental destination-block binning in front of the fill (SS_B200_CSR_BIN).  Every configuration is checked
 against the first one (hop tables bit-equal, features bit-equal) before it is timed."""
 import json
 import os
@@ -28,9 +28,8 @@ torch.cuda.synchronize()
 CONFIGS = [
     ('legacy_fill', dict(fill='legacy', overlap=False, stride=None)),
     ('abs_fill', dict(fill='abs', overlap=False, stride=None)),
-    ('abs_fill+overlap_init', dict(fill='abs', overlap=True, stride=None)),
     ('abs_fill+stride1024', dict(fill='abs', overlap=False, stride=1024)),
-    ('abs_fill+overlap_init+stride1024', dict(fill='abs', overlap=True, stride=1024)),
+    ('abs_fill+stride1024+binned_fill', dict(fill='abs', overlap=False, stride=1024, bin=1)),
 ]
 
 
@@ -47,6 +46,7 @@ results = []
 ref = None
 for name, cfg in CONFIGS:
     os.environ['SS_B200_CSR_FILL'] = cfg['fill']
+    os.environ['SS_B200_CSR_BIN'] = str(cfg.get('bin', 0))
     eh = ssb.ElphHashes(Namespace(max_hash_hops=K, floor_sf=False, minhash_num_perm=128, hll_p=8, use_zero_one=False))
     eh.overlap_init = cfg['overlap']
     eh.record_stride = cfg['stride']
