@@ -31,7 +31,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .hashing import ElphHashes, HopSketch, SketchTables, _edge_source, _ptr, _stream_ptr, check, lib
+from .hashing import (INGEST_MIN_EDGES, ElphHashes, HopSketch, SketchTables, _edge_source, _env_int, _ptr,
+                      _stream_ptr, _streamed_degree_pass, check, lib)
 
 
 def shard_bounds(num_nodes, world_size, rank):
@@ -173,9 +174,17 @@ class ShardedElphHashes(object):
                 src32 = torch.empty(G * per, dtype=torch.int32, device=device)
                 dst32 = torch.empty(G * per, dtype=torch.int32, device=device)
                 s32, d32 = src32[r * per:], dst32[r * per:]
-            check(lib.ss_csr_rowptr(_ptr(src[e_lo:e_hi]), _ptr(dst[e_lo:e_hi]), e_hi - e_lo, 0, 0, num_nodes,
-                                    _ptr(rowptr_g), _ptr(s32), _ptr(d32), _ptr(stats), _ptr(ws), ws.numel(), st),
-                  'ss_csr_rowptr')
+            if zero_copy and _env_int('SS_B200_DIST_STREAM', 0) and e_hi - e_lo >= INGEST_MIN_EDGES:
+                # EXPERIMENTAL, opt-in, unmeasured: this rank's slice through the DMA staging ring of the
+                # single-GPU build (55.6 GB/s) instead of in-place reads by the SMs (42-48 GB/s)
+                ring = _streamed_degree_pass(ei, e_hi - e_lo, 0, num_nodes, s32, d32, stats, ws, device, e_lo=e_lo)
+                check(lib.ss_csr_rowptr_finish(0, 0, num_nodes, _ptr(rowptr_g), _ptr(stats), _ptr(ws), ws.numel(), st),
+                      'ss_csr_rowptr_finish')
+                del ring  # freed in stream order: every chunk was consumed by a kernel enqueued above
+            else:
+                check(lib.ss_csr_rowptr(_ptr(src[e_lo:e_hi]), _ptr(dst[e_lo:e_hi]), e_hi - e_lo, 0, 0, num_nodes,
+                                        _ptr(rowptr_g), _ptr(s32), _ptr(d32), _ptr(stats), _ptr(ws), ws.numel(), st),
+                      'ss_csr_rowptr')
             dist.all_reduce(rowptr_g, op=dist.ReduceOp.SUM, group=self.group)
             ext = torch.stack([stats[0], -stats[3]])
             dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=self.group)

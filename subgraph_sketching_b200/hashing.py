@@ -194,9 +194,10 @@ def _ingest_stream(device):
     return _ingest_streams[key]
 
 
-def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device):
-    """pass 1 of the CSR build over a pinned host edge_index [2, E]: chunked DMA into a staging ring on the
-    ingest stream, ss_csr_degree_chunk per chunk on the current stream"""
+def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device, e_lo=0):
+    """pass 1 of the CSR build over the edges [e_lo, e_lo + n_edges) of a pinned host edge_index [2, E]: chunked
+    DMA into a staging ring on the ingest stream, ss_csr_degree_chunk per chunk on the current stream; the
+    int32 copies of edge e_lo + i land in src32[i] / dst32[i]"""
     main = torch.cuda.current_stream(device)
     copy = _ingest_stream(device)
     chunk = min(INGEST_CHUNK, n_edges)
@@ -209,8 +210,8 @@ def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats,
         with torch.cuda.stream(copy):
             if consumed[c & 1] is not None:
                 copy.wait_event(consumed[c & 1])
-            buf[0, :hi - lo].copy_(ei[0, lo:hi], non_blocking=True)  # contiguous row slices: plain DMA copies
-            buf[1, :hi - lo].copy_(ei[1, lo:hi], non_blocking=True)
+            buf[0, :hi - lo].copy_(ei[0, e_lo + lo:e_lo + hi], non_blocking=True)  # contiguous row slices: plain DMA
+            buf[1, :hi - lo].copy_(ei[1, e_lo + lo:e_lo + hi], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy)
         main.wait_event(ready)
