@@ -126,6 +126,24 @@ def test_no_gpu_means_loud_failure():
         eh.initialise_minhash(3)
 
 
+def test_neighbouring_rows_fail_loudly_without_gpu_and_keep_reference_cache_names():
+    """SIGN / heuristics: no CPU fallback either; cache file names are the reference's
+    (datasets/elph.py:120-123)"""
+    from subgraph_sketching_b200 import sign as bs
+    assert bs.feature_cache_name('root/ds', 'train', 0) == 'root/ds_train_featurecache.pt'
+    assert bs.feature_cache_name('root/ds', 'test', 2) == 'root/ds_test_k2_featurecache.pt'
+    with pytest.raises(ValueError):
+        bs.sign_features(torch.zeros(4), torch.zeros((2, 0), dtype=torch.int64), None, 0)   # x must be 2-D
+    with pytest.raises(ValueError):
+        bs.sign_features(torch.zeros(4, 2), torch.zeros((2, 0), dtype=torch.int64), None, -1)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SketchLibError):
+            bs.sign_features(torch.zeros(4, 2), torch.tensor([[0, 1], [1, 0]]), None, 1)
+        from subgraph_sketching_b200 import heuristics as bh
+        with pytest.raises(_lib.SketchLibError):
+            bh.SortedAdjacency.from_edge_index(torch.tensor([[0, 1], [1, 0]]), 2)
+
+
 def test_shape_errors_precede_device_work():
     eh = ssb.ElphHashes(make_args())
     with pytest.raises(ValueError):
