@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 11
+#define SS_ABI_VERSION 12
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -136,7 +136,28 @@ int ss_csr_rowptr(const int64_t *src, const int64_t *dst, int64_t n_edges, int64
 int ss_csr_fill(const int64_t *src, const int64_t *dst, const int32_t *src32, const int32_t *dst32, int64_t n_edges,
                 int64_t n_self_loops, const int64_t *stats, int64_t row_begin, int64_t n_rows, const int64_t *rowptr,
                 int32_t *colidx, void *workspace, int64_t workspace_bytes, ss_stream_t stream);
-/* EXPERIMENTAL, opt-in (SS_B200_CSR_BIN=1 in the Python host), not on the default path: one streaming pass that groups
+/* Streaming CSR for edge lists that are ALREADY ORDERED by the CSR key -- what PyG's coalesce / to_undirected hand the
+ * reference (datasets/elph.py:63-66, hashing.py:148): one coalesced pass, no histogram, no atomics on rows, no scattered
+ * stores.  key[] is expected non-decreasing:
+ *   key = edge_index[1], val = edge_index[0] : the exact destination-keyed CSR
+ *   key = edge_index[0], val = edge_index[1] : the source-keyed CSR, equal to the destination-keyed one iff the edge
+ *       multiset is symmetric; the pass accumulates keyed 2 x 64-bit multiset fingerprints of (key, val) and (val, key)
+ * The pass is SPECULATIVE: it never fails, it reports.  stats_io (device int64[12]) =
+ *   { max id, nnz, self loops, min id, fp(key,val) a, b, fp(val,key) a, b, key-order violations (0 = ordered),
+ *     val-order violations, range errors (id < 0, key >= n_rows, val >= 2^31), reserved }
+ * and the caller accepts rowptr / colidx only if [8] == 0, [10] == 0, max id < n_rows and (for key = edge_index[0])
+ * [4..5] == [6..7]; otherwise it falls back to ss_csr_rowptr + ss_csr_fill.  Every write is bounds-guarded
+ * (colidx_capacity entries, n_rows + 1 rowptr entries) and structural work stops at the first violation anywhere.
+ * With add_self_loops the loop of node r (every r <= max id, add_self_loops without num_nodes) is stored FIRST in
+ * row r.  A list may be fed in consecutive chunks (e_base = global index of key[0]; carry_io, device int64[2], carries
+ * the last edge across chunks; the chunk with e_base == 0 initialises stats_io); ss_csr_sorted_finish(total) completes
+ * rowptr above the last key and writes nnz / self loops into stats_io[1..2]. */
+int ss_csr_sorted_chunk(const int64_t *key, const int64_t *val, int64_t n_edges, int64_t e_base, int64_t n_rows,
+                        int add_self_loops, int64_t colidx_capacity, uint64_t fp_key_a, uint64_t fp_key_b, int64_t *rowptr,
+                        int32_t *colidx, int64_t *stats_io, int64_t *carry_io, ss_stream_t stream);
+int ss_csr_sorted_finish(int64_t n_edges_total, int64_t n_rows, int add_self_loops, int64_t colidx_capacity, int64_t *rowptr,
+                         int32_t *colidx, int64_t *stats_io, const int64_t *carry, ss_stream_t stream);
+/* EXPERIMENTAL, opt-in (SS_B200_CSR_BIN=1 in the Python host), not on the default path, MEASURED SLOWER (profiles/r02_experiments_call_a.txt: 29.3 vs 22.5 ms): one streaming pass that groups
  * the edges by destination block (dst >> shift, at most 2048 blocks; capacities = differences of rowptr) into
  * src32_out / dst32_out so that the fill walks colidx window by window and completes its 32-byte sectors in L2.
  * Writes rowptr[n_rows] - (self loops in range) entries; then call ss_csr_fill with src32 = src32_out,

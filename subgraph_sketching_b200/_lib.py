@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
 
-SS_ABI_VERSION = 11
+SS_ABI_VERSION = 12
 SS_FLAG_USE_ZERO_ONE = 1
 SS_FLAG_FLOOR = 2
 SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC, SS_MERGE_BULK = 0, 1, 2, 3, 4
@@ -49,6 +49,9 @@ SIGNATURES = {
     'ss_csr_rowptr_finish': (c_int, [c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     'ss_csr_fill': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
                             c_ptr]),
+    'ss_csr_sorted_chunk': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_i64, ctypes.c_uint64, ctypes.c_uint64, c_ptr,
+                                    c_ptr, c_ptr, c_ptr, c_ptr]),
+    'ss_csr_sorted_finish': (c_int, [c_i64, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'ss_csr_bin_workspace_bytes': (c_i64, []),
     'ss_csr_bin_edges': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                  c_ptr]),
@@ -99,7 +102,7 @@ def _load():
 # kernels enqueued by one call of each entry point (for the bench's `gpu_launches` claim); entry points
 # that return early on empty input are counted by the caller's own bookkeeping
 KERNELS_PER_CALL = {
-    'ss_init_records': 1, 'ss_pack_records': 1, 'ss_unpack_records': 1, 'ss_csr_rowptr': 4, 'ss_csr_degree_chunk': 1, 'ss_csr_rowptr_finish': 3, 'ss_csr_fill': 2, 'ss_csr_bin_edges': 1,
+    'ss_init_records': 1, 'ss_pack_records': 1, 'ss_unpack_records': 1, 'ss_csr_rowptr': 4, 'ss_csr_degree_chunk': 1, 'ss_csr_rowptr_finish': 3, 'ss_csr_fill': 2, 'ss_csr_bin_edges': 1, 'ss_csr_sorted_chunk': 1, 'ss_csr_sorted_finish': 1,
     'ss_khop_merge': 2, 'ss_khop_merge_peers': 2, 'ss_prop_min_i64': 1, 'ss_prop_max_i8': 1, 'ss_hll_count': 1, 'ss_estimate_bias': 1,
     'ss_jaccard_i64': 1, 'ss_max_i8': 1, 'ss_link_features': 1, 'ss_col_sums': 1, 'ss_common_neighbour_scores': 1,
     'ss_gcn_norm': 4, 'ss_sign_fill': 1, 'ss_sign_spmm': 1,

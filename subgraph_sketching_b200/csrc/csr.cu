@@ -307,6 +307,151 @@ __global__ void __launch_bounds__(256) bin_edges_kernel(const IdT *__restrict__ 
     }
 }
 
+// ---- streaming CSR for edge lists that are already ordered by the CSR key ------------------------------------
+// PyG's coalesce / to_undirected (what the reference's datasets hand to build_hash_tables, datasets/elph.py:63-66)
+// emit edge lists sorted by (row, col).  For such a list the CSR keyed by `key` needs no histogram, no atomics on
+// rows and no scattered stores: rowptr[r] is the position of the first edge with key >= r, colidx is the other
+// endpoint in list order -- ONE coalesced pass (read 16 B, write 4 B per edge).
+//   key = edge_index[1] (dst) : exact destination-keyed CSR
+//   key = edge_index[0] (src) : the SOURCE-keyed CSR, which equals the destination-keyed one exactly when the edge
+//                               multiset is symmetric.  The pass accumulates keyed 2 x 64-bit multiset fingerprints of
+//                               (key, val) and (val, key); the host accepts the result only if they agree (a false
+//                               accept needs a collision of a 128-bit fingerprint under a per-process random key)
+// With self loops (add_self_loops without num_nodes: one per id <= max id, hashing.py:148) the loop of row r is
+// stored FIRST in its row: every key that occurs is <= max id, so the position of edge e is e + key[e] + 1 and
+// rowptr[r] = (#edges with key < r) + r for r <= last key; ss_csr_sorted_finish completes the rows above it.
+// The pass is speculative: order violations / range errors are counted, never acted upon, and every write is
+// bounds-guarded; the host falls back to the histogram path when stats say so.
+struct SortedArgs {
+    const int64_t *key;
+    const int64_t *val;
+    int64_t n;              // edges in this chunk
+    int64_t e_base;         // global index of key[0]
+    int64_t n_rows;
+    int64_t capacity;       // entries colidx can hold
+    int loops;              // 1: implicit self loops (first in row)
+    unsigned long long ka, kb;  // fingerprint keys
+    int64_t *rowptr;
+    int32_t *colidx;
+    long long *stats;       // [12]
+    long long *carry;       // [2]: last key / last val of the previous chunk
+};
+
+__device__ __forceinline__ uint64_t fp_mix(uint64_t x) {  // murmur3 finaliser
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ uint64_t fp_second(uint64_t h) {  // non-linear in h: a second, cheaper 64-bit check
+    return (uint64_t)((uint32_t)(h >> 32) | 1u) * (uint64_t)((uint32_t)h ^ 0x9e3779b9u) + (h >> 17);
+}
+
+__global__ void __launch_bounds__(256) sorted_csr_kernel(const SortedArgs a) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long fa = 0, fb = 0, ra = 0, rb = 0;
+    long long mx = -1, mn = 0x7fffffffffffffffll;
+    unsigned bad_val = 0, bad_range = 0;
+    bool dead = false;  // an order violation was seen (by this warp or any other): the result will be discarded
+    unsigned long long *st = (unsigned long long *)a.stats;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // whole warps iterate together (the tail is padded with inactive lanes) so that shuffles are well defined
+    const int64_t n_pad = (a.n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        const bool live = i < a.n;
+        const int64_t k = live ? a.key[i] : 0;
+        const int64_t v = live ? a.val[i] : 0;
+        int64_t kp = __shfl_up_sync(FULL, k, 1);
+        int64_t vp = __shfl_up_sync(FULL, v, 1);
+        if (lane == 0) {
+            if (i > 0) { kp = a.key[i - 1]; vp = a.val[i - 1]; }
+            else if (a.e_base > 0) { kp = a.carry[0]; vp = a.carry[1]; }
+            else { kp = -1; vp = -1; }
+        }
+        const int64_t e = a.e_base + i;
+        bool ok = live;
+        if (live) {
+            mx = max(mx, (long long)max(k, v));
+            mn = min(mn, (long long)min(k, v));
+            const uint64_t hf = fp_mix((((uint64_t)k << 32) | (uint64_t)(uint32_t)v) ^ a.ka);
+            const uint64_t hr = fp_mix((((uint64_t)v << 32) | (uint64_t)(uint32_t)k) ^ a.ka);
+            fa += hf; ra += hr;
+            fb += fp_second(hf ^ a.kb); rb += fp_second(hr ^ a.kb);
+            if (v < vp) bad_val = 1;   // (only meaningful for the caller's "is the OTHER row sorted" question)
+            if (k < 0 || k >= a.n_rows || (uint64_t)v >= (1ull << 31)) { bad_range = 1; ok = false; }
+            if (kp < -1 || kp >= a.n_rows) ok = false;
+        }
+        // The pass is speculative.  On an unordered list the "rows that start here" ranges below are garbage and
+        // could add up to E * n_rows writes, so all structural work stops as soon as ANY warp has seen a violation
+        // (each 32-edge window is checked before it is acted upon; the global counter is polled once per window).
+        const bool viol = __any_sync(FULL, live && k < kp);
+        if (viol && !dead && lane == 0) atomicAdd(st + 8, 1ull);
+        dead = dead || viol;
+        if (!dead) dead = __any_sync(FULL, *(volatile unsigned long long *)(st + 8) != 0ull);
+        if (dead) {
+            if (live && i == a.n - 1) { a.carry[0] = k; a.carry[1] = v; }
+            continue;
+        }
+        // rows (kp, k] start at this edge.  Short gaps inline; long ones (runs of rows without edges) warp-wide
+        const int64_t gap = (ok && k > kp) ? (k - kp) : 0;
+        if (gap > 0 && gap <= 4) {
+            for (int64_t r = kp + 1; r <= k; ++r) {
+                const int64_t pos = e + (a.loops ? r : 0);
+                a.rowptr[r] = pos;
+                if (a.loops && pos < a.capacity) a.colidx[pos] = (int32_t)r;
+            }
+        }
+        unsigned longs = __ballot_sync(FULL, gap > 4);
+        while (longs) {
+            const int b = __ffs(longs) - 1;
+            longs &= longs - 1;
+            const int64_t r0 = __shfl_sync(FULL, kp, b) + 1, r1 = __shfl_sync(FULL, k, b), eb = __shfl_sync(FULL, e, b);
+            for (int64_t r = r0 + lane; r <= r1; r += 32) {
+                const int64_t pos = eb + (a.loops ? r : 0);
+                a.rowptr[r] = pos;
+                if (a.loops && pos < a.capacity) a.colidx[pos] = (int32_t)r;
+            }
+        }
+        if (ok) {
+            const int64_t pos = e + (a.loops ? k + 1 : 0);
+            if (pos < a.capacity) a.colidx[pos] = (int32_t)v;
+        }
+        if (live && i == a.n - 1) { a.carry[0] = k; a.carry[1] = v; }  // read by the next chunk (stream order)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fa += __shfl_xor_sync(FULL, fa, o); fb += __shfl_xor_sync(FULL, fb, o);
+        ra += __shfl_xor_sync(FULL, ra, o); rb += __shfl_xor_sync(FULL, rb, o);
+        mx = max(mx, __shfl_xor_sync(FULL, mx, o)); mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+    }
+    bad_val = __any_sync(FULL, bad_val); bad_range = __any_sync(FULL, bad_range);
+    if (lane == 0) {
+        if (mx >= 0) atomicMax(a.stats + 0, mx);
+        if (mn != 0x7fffffffffffffffll) atomicMin(a.stats + 3, mn);
+        atomicAdd(st + 4, fa); atomicAdd(st + 5, fb); atomicAdd(st + 6, ra); atomicAdd(st + 7, rb);
+        if (bad_val) atomicAdd(st + 9, 1ull);
+        if (bad_range) atomicAdd(st + 10, 1ull);
+    }
+}
+
+// rows above the last key: r in (last, n_rows]: rowptr[r] = E + min(r, L), self loops of (last, L); nnz, loop count
+__global__ void __launch_bounds__(256) sorted_csr_finish_kernel(int64_t n_edges, int64_t n_rows, int64_t capacity, int loops,
+                                                                 int64_t *rowptr, int32_t *colidx, long long *stats,
+                                                                 const long long *carry) {
+    int64_t last = n_edges > 0 ? carry[0] : -1;
+    last = last < -1 ? -1 : (last > n_rows ? n_rows : last);
+    const int64_t L = loops ? (int64_t)stats[0] + 1 : 0;  // max id + 1
+    for (int64_t r = last + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        if (r < 0) continue;
+        const int64_t pos = n_edges + (r < L ? r : L);
+        rowptr[r] = pos;
+        if (r < L && r < n_rows && pos < capacity) colidx[pos] = (int32_t)r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[1] = n_edges + (L < n_rows ? L : n_rows);  // nnz (only meaningful when max id < n_rows)
+        stats[2] = L;
+    }
+}
+
 // SS_B200_CSR_FILL=legacy keeps zero-based cursors + a rowptr read per edge (the first version)
 static bool abs_cursor_fill() {
     const char *e = getenv("SS_B200_CSR_FILL");
@@ -430,6 +575,48 @@ int ss_csr_bin_edges(const int64_t *src, const int64_t *dst, const int32_t *src3
         ss::bin_edges_kernel<int64_t><<<grid, 256, 0, st>>>(src, dst, n_edges, n_self_loops, stp, row_begin, n_rows, shift,
                                                             n_buckets, rowptr, cur, src32_out, dst32_out);
     SS_LAUNCH_CHECK("bin_edges_kernel");
+    return SS_OK;
+}
+
+// ---- streaming CSR of a key-ordered edge list (see sorted_csr_kernel) --------------------------------------------
+int ss_csr_sorted_chunk(const int64_t *key, const int64_t *val, int64_t n_edges, int64_t e_base, int64_t n_rows,
+                        int add_self_loops, int64_t colidx_capacity, uint64_t fp_key_a, uint64_t fp_key_b, int64_t *rowptr,
+                        int32_t *colidx, int64_t *stats_io, int64_t *carry_io, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && e_base >= 0 && n_rows >= 0 && colidx_capacity >= 0, "negative size passed to ss_csr_sorted_chunk");
+    SS_REQUIRE(rowptr && colidx && stats_io && carry_io, "null pointer passed to ss_csr_sorted_chunk");
+    SS_REQUIRE(n_edges == 0 || (key && val), "key/val is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e_base == 0) {
+        const long long init[12] = {-1, 0, 0, 0x7fffffffffffffffll, 0, 0, 0, 0, 0, 0, 0, 0};
+        SS_CUDA(cudaMemcpyAsync(stats_io, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    if (n_edges == 0) return SS_OK;
+    ss::SortedArgs a;
+    a.key = key; a.val = val; a.n = n_edges; a.e_base = e_base; a.n_rows = n_rows; a.capacity = colidx_capacity;
+    a.loops = add_self_loops ? 1 : 0; a.ka = fp_key_a; a.kb = fp_key_b; a.rowptr = rowptr; a.colidx = colidx;
+    a.stats = (long long *)stats_io; a.carry = (long long *)carry_io;
+    int64_t blocks = (n_edges + 255) / 256;
+    int64_t cap = (int64_t)ss::sm_count() * 8;
+    ss::sorted_csr_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a);
+    SS_LAUNCH_CHECK("sorted_csr_kernel");
+    return SS_OK;
+}
+
+int ss_csr_sorted_finish(int64_t n_edges_total, int64_t n_rows, int add_self_loops, int64_t colidx_capacity, int64_t *rowptr,
+                         int32_t *colidx, int64_t *stats_io, const int64_t *carry, ss_stream_t stream) {
+    SS_REQUIRE(n_edges_total >= 0 && n_rows >= 0, "negative size passed to ss_csr_sorted_finish");
+    SS_REQUIRE(rowptr && colidx && stats_io && carry, "null pointer passed to ss_csr_sorted_finish");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_edges_total == 0) {
+        const long long init[12] = {-1, 0, 0, 0x7fffffffffffffffll, 0, 0, 0, 0, 0, 0, 0, 0};
+        SS_CUDA(cudaMemcpyAsync(stats_io, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    int64_t blocks = (n_rows + 256) / 256;
+    int64_t cap = (int64_t)ss::sm_count() * 8;
+    ss::sorted_csr_finish_kernel<<<(int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap), 256, 0, st>>>(
+        n_edges_total, n_rows, colidx_capacity, add_self_loops ? 1 : 0, rowptr, colidx, (long long *)stats_io,
+        (const long long *)carry);
+    SS_LAUNCH_CHECK("sorted_csr_finish_kernel");
     return SS_OK;
 }
 

@@ -285,6 +285,224 @@ __global__ void __launch_bounds__(256, 3) link_features_kernel(const LinkArgs a)
     }
 }
 
+// ---- batched front end (default): tiles of consecutive links, tails and algebra evaluated for a whole batch --------
+// The per-link kernel above spends ~280 of its ~970 warp instructions per link (K = 3) in code that only 9 or 15
+// lanes execute: the K^2 scalar tails (linear counting / raw estimate / 6-NN bias search) and the inclusion-
+// exclusion algebra.  Here a warp owns a TILE of consecutive links and walks it in batches of B = 32 / K^2 links:
+// the elementwise part of each link leaves its K^2 raw statistics (matches, zero count, fixed-point sum) in the
+// slot lanes j*K^2 .. j*K^2 + K^2 - 1 of the batch, then ONE pass of the tail code serves all B*K^2 combinations and
+// one pass of the algebra (lane j = link j of the batch) serves all B links; features leave through a shared-memory
+// transpose as one contiguous store.  Consecutive links with the same source (the reference's ranking evaluation:
+// 1 positive + 1000 negatives per source, data.py:226-230) reuse u's K prepared records instead of re-loading them.
+constexpr int LK_TILE_MAX = 96;  // links per tile: a multiple of B for K = 1, 2, 3 (B = 32, 8, 3)
+
+struct RowRegsB {
+    uint4 mh;
+    uint2 he, ho;   // even-byte plane, odd-byte plane shifted down: register value in the LOW byte of each 16-bit lane
+    uint32_t nz;
+};
+
+__device__ __forceinline__ void prep_row_b(RowRegsB &r, const uint4 &m, const uint2 &h, uint32_t &big) {
+    r.mh = m;
+    r.he = make_uint2(h.x & 0x00ff00ffu, h.y & 0x00ff00ffu);
+    r.ho = make_uint2((h.x >> 8) & 0x00ff00ffu, (h.y >> 8) & 0x00ff00ffu);
+    const uint32_t nzx = ((h.x + 0x7f7f7f7fu) | h.x) & 0x80808080u;
+    const uint32_t nzy = ((h.y + 0x7f7f7f7fu) | h.y) & 0x80808080u;
+    r.nz = nzx | (nzy >> 1);
+    big |= (((h.x + 0x63636363u) | h.x) | ((h.y + 0x63636363u) | h.y)) & 0x80808080u;  // any register > 28
+}
+
+// 1 if x != 0 else 0 as ONE min instruction.  Written as opaque PTX: left to the compiler, min(x ^ y, 1) is turned back
+// into a compare + predicated moves (3 instructions per MinHash slot instead of 2).
+__device__ __forceinline__ uint32_t lk_nonzero(uint32_t x) {
+    uint32_t r;
+    asm("min.u32 %0, %1, 1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+__device__ __forceinline__ int lk_select3(int idx, int a0, int a1, int a2) { return idx == 0 ? a0 : (idx == 1 ? a1 : a2); }
+
+__device__ __forceinline__ void lk_cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void lk_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int K>
+__global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const LinkArgs a, const int tile) {
+    constexpr int C = K * K;
+    constexpr int B = 32 / C;
+    constexpr int F = K * (K + 2);
+    constexpr int EQW = (C + 3) / 4, NZW = (C + 2) / 3;
+    __shared__ float stage_all[8][B * F];
+    // endpoints of the current and the next tile of every warp (cp.async: no register staging, the load of the
+    // next tile -- a PCIe round trip when the link list is a pinned host buffer -- overlaps the current tile)
+    __shared__ __align__(16) longlong2 ids_all[8][2][LK_TILE_MAX];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float *stage = stage_all[warp];
+    const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n_tiles = (int)((a.n_links + tile - 1) / tile);  // the host keeps n_links / tile below 2^31
+    // which combination / batch slot this lane serves in the batched tail
+    const int my_j = lane / C;              // link of the batch (>= B for the idle lanes of K = 3)
+    const int my_c = lane - my_j * C;
+
+    auto fetch_ids = [&](int t, int buf) {
+        const int64_t base = (int64_t)t * tile;
+        const int cnt = (int)min((int64_t)tile, a.n_links - base);
+        for (int x = lane; x < cnt; x += 32)
+            lk_cp_async16(smem_u32(&ids_all[warp][buf][x]), reinterpret_cast<const longlong2 *>(a.links) + base + x);
+    };
+    int buf = 0;
+    if (gwarp < n_tiles) fetch_ids(gwarp, 0);
+
+    for (int t = gwarp; t < n_tiles; t += n_warps) {
+        lk_cp_async_wait();
+        __syncwarp();
+        if (t + n_warps < n_tiles) fetch_ids(t + n_warps, buf ^ 1);
+        longlong2 *ids = ids_all[warp][buf];
+        buf ^= 1;
+        const int cnt = (int)min((int64_t)tile, a.n_links - (int64_t)t * tile);
+        // bounds-check the tile's endpoints once (the reference would raise IndexError); from here on they are int32
+        for (int x = lane; x < cnt; x += 32) {
+            const longlong2 e = ids[x];
+            reinterpret_cast<int2 *>(ids + x)[0] = make_int2((int)checked_node(a, e.x), (int)checked_node(a, e.y));
+        }
+        __syncwarp();
+        RowRegsB U[K];
+        uint32_t big_u = 0;
+        int u_cur = -1;
+        for (int b0 = 0; b0 < cnt; b0 += B) {
+            const int nb = min(B, cnt - b0);
+            uint32_t my_lo = 0, my_hi = 0, my_match = 0;
+            int my_zeros = 0;
+            float my_Sx = -1.f;  // >= 0: exact-path sum (some register > 28)
+#pragma unroll 1
+            for (int j = 0; j < nb; ++j) {
+                const int2 e = reinterpret_cast<const int2 *>(ids + b0 + j)[0];  // broadcast read
+                const int u = e.x, v = e.y;
+                if (u != u_cur) {  // warp-uniform: a run of links with the same source keeps u's prepared records
+                    u_cur = u;
+                    big_u = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const uint8_t *ru = a.hop[k + 1] + (int64_t)u * a.stride[k + 1];
+                        const uint4 m = ld_nc_u4(ru + lane * 16);
+                        const uint2 h = ld_nc_u2(ru + REC_MH + lane * 8);
+                        prep_row_b(U[k], m, h, big_u);
+                    }
+                }
+                RowRegsB V[K];
+                uint32_t big = big_u;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint8_t *rv = a.hop[k + 1] + (int64_t)v * a.stride[k + 1];
+                    const uint4 m = ld_nc_u4(rv + lane * 16);
+                    const uint2 h = ld_nc_u2(rv + REC_MH + lane * 8);
+                    prep_row_b(V[k], m, h, big);
+                }
+                const bool any_big = __any_sync(FULL, big != 0u);
+                const bool mine = (my_j == j);
+                const int my_slot = mine ? my_c : -1;  // combination this lane keeps for this link
+
+                uint32_t eq_pack[EQW] = {0}, nz_pack[NZW] = {0};
+#pragma unroll
+                for (int k1 = 0; k1 < K; ++k1) {
+#pragma unroll
+                    for (int k2 = 0; k2 < K; ++k2) {
+                        const int c = k1 * K + k2;
+                        // mismatching slots: min(x ^ y, 1) summed (XOR + VIMNMX per slot, IADD3 for the sums)
+                        const uint32_t ne = lk_nonzero(U[k1].mh.x ^ V[k2].mh.x) + lk_nonzero(U[k1].mh.y ^ V[k2].mh.y) +
+                                            lk_nonzero(U[k1].mh.z ^ V[k2].mh.z) + lk_nonzero(U[k1].mh.w ^ V[k2].mh.w);
+                        eq_pack[c / 4] += ne << (8 * (c % 4));  // MISmatches; turned into matches at extraction
+                        nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
+                    }
+                }
+                if (!any_big) {
+#pragma unroll
+                    for (int k1 = 0; k1 < K; ++k1) {
+#pragma unroll
+                        for (int k2 = 0; k2 < K; ++k2) {
+                            const int c = k1 * K + k2;
+                            const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
+                            const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
+                            const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_even(ox) + pow_sum_even(oy);
+                            const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
+                            const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
+                            if (my_slot == c) { my_lo = lo; my_hi = hi; }
+                        }
+                    }
+                } else {  // rare: exact 128-bit path, combination by combination
+#pragma unroll 1
+                    for (int c = 0; c < C; ++c) {
+                        const int k1 = c / K, k2 = c % K;
+                        uint2 ue = make_uint2(0u, 0u), uo = ue, ve = ue, vo = ue;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            if (k == k1) { ue = U[k].he; uo = U[k].ho; }
+                            if (k == k2) { ve = V[k].he; vo = V[k].ho; }
+                        }
+                        uint64_t acc = 0;
+                        int nz = 0, zeros;
+                        acc_regs_word(__vmaxu2(ue.x, ve.x) | (__vmaxu2(uo.x, vo.x) << 8), acc, nz);
+                        acc_regs_word(__vmaxu2(ue.y, ve.y) | (__vmaxu2(uo.y, vo.y) << 8), acc, nz);
+                        unsigned __int128 tot = warp_total_units(acc, nz, zeros);
+                        const float S = units_to_f32(tot);
+                        if (my_slot == c) my_Sx = S;
+                    }
+                }
+                uint32_t eq_r[3] = {0, 0, 0}, nz_r[3] = {0, 0, 0};
+#pragma unroll
+                for (int w = 0; w < EQW; ++w) eq_r[w] = __reduce_add_sync(FULL, eq_pack[w]);
+#pragma unroll
+                for (int w = 0; w < NZW; ++w) nz_r[w] = __reduce_add_sync(FULL, nz_pack[w]);
+                if (mine) {
+                    const int nz_w = my_c / 3;
+                    my_match = 128u - (((uint32_t)lk_select3(my_c >> 2, (int)eq_r[0], (int)eq_r[1], (int)eq_r[2]) >> (8 * (my_c & 3))) & 0xffu);
+                    my_zeros = 256 - (int)(((uint32_t)lk_select3(nz_w, (int)nz_r[0], (int)nz_r[1], (int)nz_r[2]) >>
+                                            (10 * (my_c - 3 * nz_w))) & 0x3ffu);
+                }
+            }
+            // ---- batched tails: lane (j, c) finishes combination c of link j
+            float my_inter = 0.f;
+            if (lane < nb * C) {
+                // lo < 2^21 and hi < 2^20 are exact in float32 and so is hi * 2^16: one rounding in the add gives the
+                // correctly rounded total
+                float S = my_Sx;
+                if (S < 0.f)
+                    S = __fmul_rn(__fadd_rn(__fmul_rn((float)my_hi, 65536.f), (float)my_lo), 3.7252902984619140625e-09f);
+                my_inter = intersection_tail(a.h, my_zeros, S, my_match, 128);
+            }
+            const int64_t i0 = (int64_t)t * tile + b0;
+            if (a.inter && lane < nb * C) a.inter[i0 * C + lane] = my_inter;  // contiguous: consecutive links
+            if (a.features) {
+                // ---- batched algebra: lane j = link j of the batch
+                const int jj = lane < nb ? lane : 0;
+                float I[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, jj * C + c);
+                const int2 e = reinterpret_cast<const int2 *>(ids + b0 + jj)[0];
+                const int64_t u = e.x, v = e.y;
+                float cu[K], cv[K], f[F];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    cu[k] = __ldg(a.cards + u * a.cards_stride + k);
+                    cv[k] = __ldg(a.cards + v * a.cards_stride + k);
+                }
+                feature_algebra<K>(I, cu, cv, f);
+                knockout_and_floor<K>(f, a.flags);
+                __syncwarp();
+                if (lane < nb) {
+#pragma unroll
+                    for (int x = 0; x < F; ++x) stage[lane * F + x] = f[x];
+                }
+                __syncwarp();
+                for (int x = lane; x < nb * F; x += 32) a.features[i0 * F + x] = stage[x];
+            }
+        }
+    }
+}
+
 // ---- TMA front end: links are processed in PAIRS; for each hop ONE gather4 (UTMALDG.2D.GATHER4) fetches
 // the four records (uA, vA, uB, vB) of the pair into the warp's shared-memory stage, two stages deep, so the
 // 12 records of the next pair are in flight while the current pair is being evaluated -- the load latency
@@ -486,6 +704,12 @@ static EncodeTiledFn lk_encode_fn() {
 // which front end.  Measured on B200 (R-MAT 24, K=3, 20 M links): LDG 27.8 ms, TMA pairs 37.2 ms -- the kernel is
 // instruction-bound (~900 warp instructions per link) and the TMA stages cap residency at 12 warps / SM, so
 // hiding the load latency does not pay for the lost issue slots.  LDG is the default; SS_B200_LINKS=tma opts in.
+// SS_B200_LINKS=ldg: the round-1 kernel (one link per warp at a time, tails per link)
+static bool want_per_link_kernel() {
+    const char *e = getenv("SS_B200_LINKS");
+    return e && e[0] == 'l';
+}
+
 static bool want_tma_links() {
     const char *e = getenv("SS_B200_LINKS");
     if (!(e && e[0] == 't')) return false;
@@ -524,9 +748,26 @@ static int launch_links(const LinkArgs &a, const int64_t *hop_rows, bool fast, c
         int64_t resident = (int64_t)per_sm * sm_count();
         k<<<(int)(want < resident ? want : resident), LK_WARPS * 32, smem, st>>>(a, maps);
         SS_LAUNCH_CHECK("link_features_tma_kernel");
-    } else if (fast) {
+    } else if (fast && want_per_link_kernel()) {
         link_features_kernel<K><<<grid, 256, 0, st>>>(a);
         SS_LAUNCH_CHECK("link_features_kernel");
+    } else if (fast) {
+        // tile: a multiple of B = 32 / K^2, at most LK_TILE_MAX, small enough that every resident warp gets ~2 tiles
+        constexpr int B = 32 / (K * K);
+        const int64_t resident_warps = (int64_t)sm_count() * 3 * 8;
+        int64_t tile = a.n_links / (2 * resident_warps);
+        tile = tile / B * B;
+        if (tile < B) tile = B;
+        if (tile > LK_TILE_MAX) tile = LK_TILE_MAX;
+        if (const char *e = getenv("SS_B200_LINK_TILE")) {  // tuning knob
+            int64_t v = atoi(e) / B * B;
+            if (v >= B && v <= LK_TILE_MAX) tile = v;
+        }
+        const int64_t n_tiles = (a.n_links + tile - 1) / tile;
+        int64_t bl = (n_tiles + 7) / 8;
+        int64_t cap_b = (int64_t)sm_count() * 3;
+        link_features_batched_kernel<K><<<(int)(bl < cap_b ? bl : cap_b), 256, 0, st>>>(a, (int)tile);
+        SS_LAUNCH_CHECK("link_features_batched_kernel");
     } else {
         link_features_generic_kernel<K><<<grid, 256, 0, st>>>(a);
         SS_LAUNCH_CHECK("link_features_generic_kernel");

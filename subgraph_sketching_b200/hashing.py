@@ -88,16 +88,35 @@ def _to_host(t):
     return out
 
 
-def hllpp_tables(p):
+_warned_tables = set()
+
+
+def hllpp_tables(p, with_source=False):
     """(threshold, raw_estimate[T], bias[T]) for precision p: from `datasketch` when it is importable
     (what the reference reads, hashing.py:77-80), else from the packaged Monte-Carlo tables
-    (tools/gen_hllpp_tables.py)."""
+    (tools/gen_hllpp_tables.py) or the file named by SS_B200_HLLPP_TABLES.  The packaged tables are NOT the
+    published HLL++ constants: cardinalities between the threshold and 5m then differ from a reference run that
+    has `datasketch`, so that fallback warns once per precision (set SS_B200_HLLPP_TABLES or pass `hll_tables`
+    to choose tables explicitly).  with_source=True also returns where the tables came from."""
     try:
         from datasketch import hyperloglog_const as hc
-        return hc._thresholds[p - 4], list(hc._raw_estimate[p - 4]), list(hc._bias[p - 4])
+        out = (hc._thresholds[p - 4], list(hc._raw_estimate[p - 4]), list(hc._bias[p - 4]))
+        src = 'datasketch'
     except ImportError:
         blob = np.load(_TABLES_PATH)
-        return int(blob['thresholds'][p - 4]), blob[f'raw_estimate_p{p}'], blob[f'bias_p{p}']
+        out = (int(blob['thresholds'][p - 4]), blob[f'raw_estimate_p{p}'], blob[f'bias_p{p}'])
+        explicit = bool(os.environ.get('SS_B200_HLLPP_TABLES'))
+        src = f'file:{_TABLES_PATH}' if explicit else 'packaged-monte-carlo'
+        if not explicit and p not in _warned_tables:
+            _warned_tables.add(p)
+            import warnings
+            warnings.warn(
+                f'datasketch is not importable: using the packaged Monte-Carlo HLL++ bias tables for p={p} '
+                f'({_TABLES_PATH}).  They are substitutes for datasketch.hyperloglog_const; estimates in the '
+                'bias-corrected regime (threshold < e <= 5m) and caches derived from them differ from a reference '
+                'run that has datasketch.  Install datasketch, set SS_B200_HLLPP_TABLES, or pass hll_tables=.',
+                RuntimeWarning, stacklevel=3)
+    return out + (src,) if with_source else out
 
 
 def hll_alpha(p):
@@ -194,10 +213,58 @@ def _ingest_stream(device):
     return _ingest_streams[key]
 
 
-def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device, e_lo=0):
-    """pass 1 of the CSR build over the edges [e_lo, e_lo + n_edges) of a pinned host edge_index [2, E]: chunked
-    DMA into a staging ring on the ingest stream, ss_csr_degree_chunk per chunk on the current stream; the
-    int32 copies of edge e_lo + i land in src32[i] / dst32[i]"""
+# streaming CSR of key-ordered lists (ss_csr_sorted_chunk): tried first on lists of at least this many edges
+CSR_FAST_MIN_EDGES = 1 << 12
+_FP_KEYS = tuple(int.from_bytes(os.urandom(8), 'little') for _ in range(2))  # per-process fingerprint keys
+
+
+def _sorted_stats_ok(s, n_edges, num_rows, symmetric_needed):
+    """accept the speculative streaming CSR?  s = stats_io of ss_csr_sorted_chunk / _finish as a python list"""
+    if s[8] != 0 or s[10] != 0 or s[0] >= num_rows or (n_edges and s[3] < 0):
+        return False
+    return (not symmetric_needed) or (s[4], s[5]) == (s[6], s[7])
+
+
+def _try_sorted_csr(src, dst, n_edges, num_rows, add_loops, device, streamed_from=None, degree_side=None):
+    """speculative one-pass CSR for key-ordered edge lists (coalesced / to_undirected output) -> (rowptr, colidx, nnz,
+    max_id) or None when the list is neither (ordered by edge_index[0] AND symmetric) nor ordered by edge_index[1].
+    streamed_from: pinned host edge_index to stream through the DMA ring instead of reading src / dst;
+    degree_side(buf0, buf1, lo, hi, first): called per landed chunk (the histogram pass of the fallback rides along)."""
+    cap = n_edges + (num_rows if add_loops else 0)
+    colidx = torch.empty(max(cap, 4), dtype=torch.int32, device=device)
+    rowptr = torch.empty(num_rows + 1, dtype=torch.int64, device=device)
+    st12 = torch.empty(12, dtype=torch.int64, device=device)
+    carry = torch.empty(2, dtype=torch.int64, device=device)
+    st = _stream_ptr(device)
+    loops = 1 if add_loops else 0
+    orientations = ('src', 'dst') if streamed_from is None else ('src',)
+    for orient in orientations:
+        if streamed_from is None:
+            key, val = (src, dst) if orient == 'src' else (dst, src)
+            check(lib.ss_csr_sorted_chunk(_ptr(key), _ptr(val), n_edges, 0, num_rows, loops, cap, _FP_KEYS[0], _FP_KEYS[1],
+                                          _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry), st), 'ss_csr_sorted_chunk')
+        else:
+            ring = _stream_chunks(streamed_from, n_edges, device, lambda b0, b1, lo, hi, c: (
+                degree_side(b0, b1, lo, hi, c) if degree_side is not None else None,
+                check(lib.ss_csr_sorted_chunk(_ptr(b0), _ptr(b1), hi - lo, lo, num_rows, loops, cap, _FP_KEYS[0],
+                                              _FP_KEYS[1], _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
+                                              _stream_ptr(device)), 'ss_csr_sorted_chunk')))
+        check(lib.ss_csr_sorted_finish(n_edges, num_rows, loops, cap, _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
+                                       st), 'ss_csr_sorted_finish')
+        s = [int(v) for v in st12.tolist()]  # the one host synchronisation of the CSR build
+        if streamed_from is not None:
+            del ring
+        if _sorted_stats_ok(s, n_edges, num_rows, symmetric_needed=(orient == 'src')):
+            return rowptr, colidx, s[1], s[0]
+        if not (orient == 'src' and s[9] == 0 and s[10] == 0):
+            break  # edge_index[1] is not ordered either
+    return None
+
+
+def _stream_chunks(ei, n_edges, device, consume, e_lo=0):
+    """chunked DMA of the edges [e_lo, e_lo + n_edges) of a pinned host edge_index [2, E] into a two-slot device ring on
+    the ingest stream; consume(buf_row0, buf_row1, lo, hi, chunk_index) enqueues the kernels of a landed chunk on the
+    current stream (lo / hi relative to e_lo).  Returns the ring (keep it alive until the stream has consumed it)."""
     main = torch.cuda.current_stream(device)
     copy = _ingest_stream(device)
     chunk = min(INGEST_CHUNK, n_edges)
@@ -215,20 +282,31 @@ def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats,
             ready = torch.cuda.Event()
             ready.record(copy)
         main.wait_event(ready)
-        check(lib.ss_csr_degree_chunk(_ptr(buf[0]), _ptr(buf[1]), hi - lo, row_begin, num_rows, _ptr(src32[lo:hi]),
-                                      _ptr(dst32[lo:hi]), _ptr(stats), _ptr(ws), ws.numel(), 1 if c == 0 else 0,
-                                      _stream_ptr(device)), 'ss_csr_degree_chunk')
+        consume(buf[0], buf[1], lo, hi, c)
         consumed[c & 1] = torch.cuda.Event()
         consumed[c & 1].record(main)
-    return ring  # kept alive by the caller until the current stream has consumed it
+    return ring
+
+
+def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device, e_lo=0):
+    """pass 1 of the CSR build over the edges [e_lo, e_lo + n_edges) of a pinned host edge_index [2, E]: chunked
+    DMA into a staging ring on the ingest stream, ss_csr_degree_chunk per chunk on the current stream; the
+    int32 copies of edge e_lo + i land in src32[i] / dst32[i]"""
+    def consume(b0, b1, lo, hi, c):
+        check(lib.ss_csr_degree_chunk(_ptr(b0), _ptr(b1), hi - lo, row_begin, num_rows, _ptr(src32[lo:hi]),
+                                      _ptr(dst32[lo:hi]), _ptr(stats), _ptr(ws), ws.numel(), 1 if c == 0 else 0,
+                                      _stream_ptr(device)), 'ss_csr_degree_chunk')
+    return _stream_chunks(ei, n_edges, device, consume, e_lo=e_lo)
 
 
 def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bounds_fn=None):
-    """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [nnz], nnz, max_id) keyed by destination
+    """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [>= nnz], nnz, max_id) keyed by destination
     (PyG flow source -> target, hashing.py:30-35).  With add_loops, a self loop is appended for every node id
     < max(edge_index)+1 (computed on the device), which is add_self_loops(edge_index) without num_nodes
-    (hashing.py:148).  One device->host read (32 bytes of statistics) sizes colidx.  A pinned host edge_index
-    never gets a full-size device copy: it is streamed through a staging ring (large lists) or read in place."""
+    (hashing.py:148).  One device->host read of the statistics per attempt.  A pinned host edge_index
+    never gets a full-size device copy: it is streamed through a staging ring (large lists) or read in place.
+    Lists ordered by their CSR key (coalesced / to_undirected output) take the one-pass streaming build
+    (ss_csr_sorted_chunk); anything else the histogram + scan + cursor-fill build."""
     ei, zero_copy = _edge_source(edge_index, device)
     n_edges = ei.shape[1]
     if num_rows is None:  # rows = max id + 1: needs the id statistics first
@@ -236,7 +314,6 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
     src, dst = ei[0], ei[1]
     ws_bytes = check(lib.ss_csr_workspace_bytes(num_rows), 'ss_csr_workspace_bytes')
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=device)
-    rowptr = torch.empty(num_rows + 1, dtype=torch.int64, device=device)
     stats = torch.empty(4, dtype=torch.int64, device=device)
     src32 = dst32 = None
     if zero_copy and n_edges:
@@ -244,9 +321,27 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
         dst32 = torch.empty(n_edges, dtype=torch.int32, device=device)
     st = _stream_ptr(device)
     loops = -1 if add_loops else 0
+    streamed = zero_copy and n_edges >= INGEST_MIN_EDGES
+    fast = (_env_int('SS_B200_CSR_FAST', 1) and n_edges >= CSR_FAST_MIN_EDGES and row_begin == 0
+            and n_edges + num_rows < (1 << 40))
+    histogram_done = False
+    if fast:
+        side = None
+        if streamed:  # the histogram pass of the fallback rides along under the DMA (the SMs are idle anyway)
+            def side(b0, b1, lo, hi, c):
+                check(lib.ss_csr_degree_chunk(_ptr(b0), _ptr(b1), hi - lo, row_begin, num_rows, _ptr(src32[lo:hi]),
+                                              _ptr(dst32[lo:hi]), _ptr(stats), _ptr(ws), ws.numel(), 1 if c == 0 else 0,
+                                              _stream_ptr(device)), 'ss_csr_degree_chunk')
+        got = _try_sorted_csr(src, dst, n_edges, num_rows, add_loops, device, streamed_from=ei if streamed else None,
+                              degree_side=side)
+        if got is not None:
+            return got
+        histogram_done = streamed
+    rowptr = torch.empty(num_rows + 1, dtype=torch.int64, device=device)
     ring = None
-    if zero_copy and n_edges >= INGEST_MIN_EDGES:
-        ring = _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device)
+    if streamed:
+        if not histogram_done:
+            ring = _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats, ws, device)
         check(lib.ss_csr_rowptr_finish(loops, row_begin, num_rows, _ptr(rowptr), _ptr(stats), _ptr(ws), ws.numel(), st),
               'ss_csr_rowptr_finish')
     else:
@@ -260,8 +355,8 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
         raise IndexError('node ids must be < 2^31')
     colidx = torch.empty(max(nnz, 4), dtype=torch.int32, device=device)
     if _env_int('SS_B200_CSR_BIN', 0) and n_edges >= _env_int('SS_B200_CSR_BIN_MIN_EDGES', 1 << 22):
-        # EXPERIMENTAL, opt-in, unmeasured: group the edges by destination block first so that the fill's scattered
-        # stores stay inside an L2-resident window of colidx (csrc/csr.cu: bin_edges_kernel)
+        # EXPERIMENTAL, opt-in, measured SLOWER (profiles/r02_experiments_call_a.txt): group the edges by destination
+        # block first so that the fill's scattered stores stay inside an L2-resident window of colidx
         n_binned = nnz - min(max(n_loops_used - row_begin, 0), num_rows)
         b_src = torch.empty(max(n_binned, 1), dtype=torch.int32, device=device)
         b_dst = torch.empty(max(n_binned, 1), dtype=torch.int32, device=device)
@@ -440,8 +535,10 @@ class ElphHashes(object):
         self.alpha = hll_alpha(self.p)
         self.max_rank = 64 - self.p
         self.hll_size = self.m
+        # provenance of the HLL++ tables ('datasketch' | 'packaged-monte-carlo' | 'file:...' | 'caller')
+        self.hll_tables_source = 'caller'
         if hll_tables is None:
-            hll_tables = hllpp_tables(self.p)
+            *hll_tables, self.hll_tables_source = hllpp_tables(self.p, with_source=True)
         threshold, raw_estimate, bias = hll_tables
         self.hll_threshold = threshold
         self.bias_vector = torch.tensor(np.asarray(bias, dtype=np.float64), dtype=torch.float)
@@ -466,6 +563,7 @@ class ElphHashes(object):
         nz = torch.arange(1, self.m + 1, dtype=torch.int64)
         self._lc_host = torch.cat([torch.zeros(1), self.m * torch.log(self.m / nz)]).float()
         self._dev = {}  # per-device constants
+        self._twins = {}
 
     # ------------------------------------------------------------------ device constants
     def _consts(self, device):
@@ -689,8 +787,29 @@ class ElphHashes(object):
             if out_device == device:
                 return tables, cards
             cards_host = _to_host(cards)
-            cards_host._ss_device_copy = (cards, cards_host._version)  # spares get_subgraph_features the re-upload
+            self._remember_twin(cards_host, cards)  # spares get_subgraph_features the re-upload
             return tables, cards_host
+
+    # device twins of host tensors this engine returned.  Kept HERE (id -> (weakref, twin, version)), never on the
+    # tensor: torch.save pickles a tensor's __dict__, so an attribute would travel into the reference's cardcache.pt
+    def _remember_twin(self, host_tensor, device_tensor):
+        import weakref
+        key = id(host_tensor)
+        twins = self._twins
+
+        def _drop(_ref, key=key):
+            twins.pop(key, None)
+
+        twins[key] = (weakref.ref(host_tensor, _drop), device_tensor, host_tensor._version)
+
+    def _twin_of(self, host_tensor, device):
+        ent = self._twins.get(id(host_tensor))
+        if ent is None:
+            return None
+        ref, twin, version = ent
+        if ref() is not host_tensor or version != host_tensor._version or twin.device != device:
+            return None
+        return twin
 
     # ------------------------------------------------------------------ K4
     def _hop_views(self, hash_table, device):
@@ -778,14 +897,17 @@ class ElphHashes(object):
         F = K * (K + 2)
         with torch.cuda.device(device):
             views, keep = self._hop_views(hash_table, device)
-            cached = getattr(cards, '_ss_device_copy', None)  # device twin of a cards tensor we returned to the host
-            if cached is not None and cached[1] == cards._version and cached[0].device == device:
-                cd = cached[0]
-            else:
+            cd = self._twin_of(cards, device)  # device twin of a cards tensor we returned to the host
+            if cd is None:
                 cd = cards.to(device, non_blocking=True) if cards.device != device else cards
                 cd = (cd if cd.dtype == torch.float32 else cd.float()).contiguous()
             if cd.dim() != 2 or cd.shape[1] < K:
                 raise ValueError('cards must be [n_nodes, max_hops]')
+            n_table_rows = min(int(views[k].num_rows) for k in range(1, K + 1))
+            if cd.shape[0] < n_table_rows:
+                # the kernel bounds-checks link endpoints against the hop tables only; the reference would raise
+                # IndexError from cards[links[:, 0]] (hashing.py:274)
+                raise IndexError(f'cards has {cd.shape[0]} rows but the hash tables have {n_table_rows}')
             ld = self._link_source(links, device)
             n = ld.shape[0]
             d = self._consts(device)

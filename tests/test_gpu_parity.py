@@ -425,23 +425,44 @@ def test_full_size_properties_rmat24():
 
 
 def test_link_feature_front_ends_agree(monkeypatch):
-    """the TMA-pair front end (opt-in) must give the bits of the default LDG front end, odd link counts included"""
+    """the batched kernel (default: tiles of consecutive links, tails / algebra per batch, source records reused along
+    runs of equal sources), the per-link kernel (SS_B200_LINKS=ldg) and the TMA-pair front end (=tma) give the same
+    bits -- odd link counts, every tile size, random and source-grouped link lists"""
     n = 1 << 13
     ei = rmat_edges(13, 8, 5).to(DEV)
     g = torch.Generator().manual_seed(2)
     for K in (1, 2, 3):
         eh = ssb.ElphHashes(make_args(K, use_zero_one=True))
         tables, cards = eh.build_hash_tables(n, ei)
-        for L in (1, 2, 7, 4097):
+        for L in (1, 2, 7, 100, 4097):
             links = torch.randint(0, n, (L, 2), generator=g).to(DEV)
-            monkeypatch.setenv('SS_B200_LINKS', 'ldg')
-            a = eh.get_subgraph_features(links, tables, cards)
-            ia = eh._get_intersections(links, tables)
-            monkeypatch.setenv('SS_B200_LINKS', 'tma')
-            b = eh.get_subgraph_features(links, tables, cards)
-            ib = eh._get_intersections(links, tables)
-            assert torch.equal(a, b), (K, L)
-            assert all(torch.equal(ia[k], ib[k]) for k in ia)
+            grouped = links.clone()
+            grouped[:, 0] = links[torch.arange(L, device=DEV) // 37, 0]   # runs of 37 links per source
+            for lk in (links, grouped):
+                monkeypatch.setenv('SS_B200_LINKS', 'ldg')
+                a = eh.get_subgraph_features(lk, tables, cards)
+                ia = eh._get_intersections(lk, tables)
+                monkeypatch.setenv('SS_B200_LINKS', 'tma')
+                b = eh.get_subgraph_features(lk, tables, cards)
+                ib = eh._get_intersections(lk, tables)
+                assert torch.equal(a, b), (K, L)
+                assert all(torch.equal(ia[k], ib[k]) for k in ia)
+                monkeypatch.delenv('SS_B200_LINKS')
+                for tile in (None, 3, 8, 24, 32, 96):
+                    if tile is None:
+                        monkeypatch.delenv('SS_B200_LINK_TILE', raising=False)
+                    else:
+                        monkeypatch.setenv('SS_B200_LINK_TILE', str(tile))
+                    c = eh.get_subgraph_features(lk, tables, cards)
+                    ic = eh._get_intersections(lk, tables)
+                    assert torch.equal(a, c), (K, L, tile)
+                    assert all(torch.equal(ia[k], ic[k]) for k in ia), (K, L, tile)
+                monkeypatch.delenv('SS_B200_LINK_TILE', raising=False)
+    # out-of-range endpoints are flagged by the batched kernel too
+    with pytest.raises(IndexError):
+        eh.get_subgraph_features(torch.tensor([[0, 1], [2, n]], device=DEV), tables, cards)
+    with pytest.raises(IndexError):
+        eh.get_subgraph_features(torch.tensor([[-1, 1]], device=DEV), tables, cards)
 
 
 def test_pinned_host_inputs_are_read_in_place(monkeypatch):
@@ -604,11 +625,83 @@ def test_layout_and_scheduling_knobs_are_bit_equal(monkeypatch):
         eh.build_hash_tables(n, ei)
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('SS_TEST_EXPERIMENTAL'),
-                    reason='opt-in: experimental, not yet measured paths (set SS_TEST_EXPERIMENTAL=1)')
+def _adjacency_key(csr, n):
+    """sorted (row, neighbour) multiset of a (rowptr, colidx, nnz, max_id) tuple"""
+    rowptr, colidx, nnz, _ = csr
+    assert int(rowptr[0]) == 0 and int(rowptr[-1]) == nnz
+    rows = torch.repeat_interleave(torch.arange(rowptr.numel() - 1, device=rowptr.device), rowptr[1:] - rowptr[:-1])
+    return torch.sort(rows * n + colidx[:nnz].long()).values
+
+
+def test_streaming_csr_of_key_ordered_lists(monkeypatch):
+    """ss_csr_sorted_chunk (one-pass CSR of lists ordered by their CSR key, the default for coalesced / to_undirected
+    input) gives the same adjacency as the histogram + fill build: symmetric lists ordered by source, asymmetric lists
+    ordered by destination, long runs of isolated rows, ids above max(edge_index), with and without self loops, device
+    and streamed pinned-host input; lists that are not eligible (ordered by source but asymmetric, shuffled) fall back"""
+    import subgraph_sketching_b200.hashing as H
+    dev = torch.device(DEV)
+    n = 1 << 15
+    sym = rmat_edges(15, 16, 7, dev)                                   # sorted by (src, dst), symmetric
+    g = torch.Generator(device=dev).manual_seed(3)
+    asym = sym[:, torch.rand(sym.shape[1], generator=g, device=dev) < 0.5]           # ordered by src only
+    by_dst = torch.stack([asym[1], asym[0]])                              # asymmetric, ordered by edge_index[1]
+    gaps = torch.cat([sym[:, sym[0] < 100], sym[:, sym[0] > 20000] ], dim=1)           # long run of rows without edges
+    gaps = gaps[:, (gaps[1] < 100) | (gaps[1] > 20000)]
+    shuffled = sym[:, torch.randperm(sym.shape[1], generator=g, device=dev)]
+    cases = {'symmetric': (sym, True), 'ordered by dst': (by_dst, True), 'isolated runs': (gaps, True),
+             'asymmetric ordered by src': (asym, False), 'shuffled': (shuffled, False)}
+    calls = []
+    real = H._try_sorted_csr
+
+    def spy(*a, **kw):
+        out = real(*a, **kw)
+        calls.append(out is not None)
+        return out
+
+    monkeypatch.setattr(H, '_try_sorted_csr', spy)
+    for name, (ei, eligible) in cases.items():
+        for rows, loops in ((n, True), (n + 777, True), (n, False)):
+            monkeypatch.setenv('SS_B200_CSR_FAST', '0')
+            want = ssb.build_csr(ei, dev, num_rows=rows, add_loops=loops)
+            monkeypatch.setenv('SS_B200_CSR_FAST', '1')
+            calls.clear()
+            got = ssb.build_csr(ei, dev, num_rows=rows, add_loops=loops)
+            assert calls == [eligible], (name, calls)
+            assert got[2] == want[2] and got[3] == want[3], name
+            assert torch.equal(got[0], want[0]), name
+            assert torch.equal(_adjacency_key(got, n + 777), _adjacency_key(want, n + 777)), name
+    # streamed pinned-host input: chunks of 4096 edges through the DMA ring, histogram pass riding along
+    monkeypatch.setattr(H, 'INGEST_MIN_EDGES', 1 << 10)
+    monkeypatch.setattr(H, 'INGEST_CHUNK', 1 << 12)
+    for name in ('symmetric', 'isolated runs', 'shuffled', 'asymmetric ordered by src'):
+        ei, eligible = cases[name]
+        monkeypatch.setenv('SS_B200_CSR_FAST', '0')
+        want = ssb.build_csr(ei, dev, num_rows=n, add_loops=True)
+        monkeypatch.setenv('SS_B200_CSR_FAST', '1')
+        calls.clear()
+        got = ssb.build_csr(ei.cpu().pin_memory(), dev, num_rows=n, add_loops=True)
+        assert calls == [eligible], (name, calls)
+        assert got[2] == want[2] and torch.equal(got[0], want[0]), name
+        assert torch.equal(_adjacency_key(got, n), _adjacency_key(want, n)), name
+    # out-of-range ids still raise through the fallback
+    bad = sym.clone()
+    bad[1, -1] = n + 5
+    with pytest.raises(IndexError):
+        ssb.ElphHashes(make_args(1)).build_hash_tables(n, bad)
+    # and the tables do not depend on which build produced the adjacency
+    eh = ssb.ElphHashes(make_args(2))
+    t1, c1 = eh.build_hash_tables(n, sym)
+    monkeypatch.setenv('SS_B200_CSR_FAST', '0')
+    t0, c0 = eh.build_hash_tables(n, sym)
+    for k in range(3):
+        assert torch.equal(t1.records(k), t0.records(k))
+    assert torch.equal(c1, c0)
+
+
 def test_experimental_binned_csr_fill_is_equivalent(monkeypatch):
-    """SS_B200_CSR_BIN=1 (edges grouped by destination block before the fill) must give the same adjacency: equal
-    rowptr, equal neighbour multiset per row, bit-equal tables -- device and pinned-host inputs, row ranges"""
+    """SS_B200_CSR_BIN=1 (edges grouped by destination block before the fill; opt-in, measured slower) must give the same
+    adjacency: equal rowptr, equal neighbour multiset per row, bit-equal tables -- device and pinned-host inputs, row ranges"""
+    monkeypatch.setenv('SS_B200_CSR_FAST', '0')
     n = 1 << 15
     dev = torch.device(DEV)
     ei = rmat_edges(15, 16, 6, dev)
