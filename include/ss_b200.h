@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 12
+#define SS_ABI_VERSION 13
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -50,6 +50,7 @@ extern "C" {
 #define SS_MERGE_BULK 4         /* one 1-D cp.async.bulk per row into the same ring (P=128, p=8) */
 
 typedef void *ss_stream_t;
+#define SS_MAX_PEERS 7   /* peers of one GPU in the fused multi-GPU exchange (8 GPUs per box) */
 
 /*
  * HyperLogLog++ constants for one precision p.  They are INPUTS (the reference takes them from
@@ -104,6 +105,18 @@ int ss_pack_records(const int64_t *minhash, const int8_t *hll, int64_t n, int nu
                     void *rec_out, int64_t out_stride, ss_stream_t stream);
 int ss_unpack_records(const void *rec, int64_t rec_stride, int64_t n, int num_perm, int hll_p,
                       int64_t *minhash_out, int8_t *hll_out, ss_stream_t stream);
+/* the same with
+ *   error_flag (device int32[2] initialised to {0, 1} by the caller, or NULL): when a value does not fit a record (MinHash
+ *              outside [0, 2^32), register outside [0, 127]) [0] is set to 1 and [1] cleared to 0.  A host that did not
+ *              synchronise to inspect the tensor first enqueues the record engine guarded by &flag[1] and the plain
+ *              int64 kernel (ss_prop_min_i64_guarded) guarded by &flag[0]: exactly one of them runs (the reference's
+ *              sketches always fit: hashing.py:59,122, :132-136)
+ *   guard      (device int32 or NULL): the kernel returns at once when *guard == 0 (see ss_khop_merge_ex)
+ * and, when only one side of the pair is given, a row stride as narrow as that side (512-byte MinHash-only tables). */
+int ss_pack_records_ex(const int64_t *minhash, const int8_t *hll, int64_t n, int num_perm, int hll_p, void *rec_out,
+                       int64_t out_stride, int32_t *error_flag, const int32_t *guard, ss_stream_t stream);
+int ss_unpack_records_ex(const void *rec, int64_t rec_stride, int64_t n, int num_perm, int hll_p, int64_t *minhash_out,
+                         int8_t *hll_out, const int32_t *guard, ss_stream_t stream);
 
 /* ---- K6: COO -> CSR keyed by destination ------------------------------------------------------
  * The reference scatters over the COO edge_index with self loops appended by
@@ -157,6 +170,40 @@ int ss_csr_sorted_chunk(const int64_t *key, const int64_t *val, int64_t n_edges,
                         int32_t *colidx, int64_t *stats_io, int64_t *carry_io, ss_stream_t stream);
 int ss_csr_sorted_finish(int64_t n_edges_total, int64_t n_rows, int add_self_loops, int64_t colidx_capacity, int64_t *rowptr,
                          int32_t *colidx, int64_t *stats_io, const int64_t *carry, ss_stream_t stream);
+/* Row-block forms for the node-sharded build: in a list ordered by its key the edges of the rows
+ * [row_begin, row_begin + n_rows) are ONE contiguous slice [e_origin, e_origin + n_edges_total) of the list, so every rank
+ * streams only its own slice (also over PCIe when the list is in pinned host memory) -- no histogram all-reduce, no
+ * pass over the whole list.  rowptr (n_rows + 1 entries) and colidx positions are local to the block; stats_io[0] (max id)
+ * must hold the GLOBAL maximum when ss_csr_sorted_finish_rows runs (all-reduce it between the two calls), and the
+ * fingerprints / violation counters are summed over ranks before the verdict.
+ * ss_csr_sorted_bounds cuts the rows into cost-balanced blocks WITHOUT a histogram: cost(r) = (#edges with key < r) +
+ * row_cost * r, cut q at cum_shares[q] (device double [n_cuts], increasing, in (0, 1)) of the total; it writes
+ * bounds_out[0..n_cuts+1] (rows) and edge_offsets_out[0..n_cuts+1] (first edge of each block), device int64.
+ * ss_mark_rows: mark[colidx[e]] = 1 -- the rows a rank's neighbour lists read, from which the owners derive the
+ * peer_mask of ss_khop_merge_ex. */
+int ss_csr_sorted_chunk_rows(const int64_t *key, const int64_t *val, int64_t n_edges, int64_t e_base, int64_t e_origin,
+                             int64_t row_begin, int64_t n_rows, int add_self_loops, int64_t colidx_capacity,
+                             uint64_t fp_key_a, uint64_t fp_key_b, int64_t *rowptr, int32_t *colidx, int64_t *stats_io,
+                             int64_t *carry_io, ss_stream_t stream);
+int ss_csr_sorted_finish_rows(int64_t n_edges_total, int64_t row_begin, int64_t n_rows, int add_self_loops,
+                              int64_t colidx_capacity, int64_t *rowptr, int32_t *colidx, int64_t *stats_io,
+                              const int64_t *carry, ss_stream_t stream);
+int ss_csr_sorted_bounds(const int64_t *key, int64_t n_edges, int64_t n_rows, double row_cost, const double *cum_shares,
+                         int n_cuts, int64_t *bounds_out, int64_t *edge_offsets_out, ss_stream_t stream);
+int ss_mark_rows(const int32_t *colidx, int64_t nnz, uint8_t *mark, ss_stream_t stream);
+/* Synchronisation-free CSR for the operator forms (the edge list already holds its self loops: ELPH.forward applies
+ * add_self_loops itself, models/elph.py:186, and calls hll_prop / minhash_prop 2K times per training batch): nnz = n_edges
+ * is known to the host, so nothing is read back.  Ids are validated on the device -- stats_out (device int64[4]) =
+ * { max id, entries kept, 0, min id }, to be inspected whenever the host next synchronises; sources outside [0, n_rows)
+ * are clamped to 0, edges with a destination outside are dropped, colidx (n_edges entries) is zero-filled first: a bad
+ * list gives wrong sketches (the reference's CUDA scatter would trip a device-side assert) but never an out-of-bounds
+ * access.  guard (device int32 or NULL): every kernel returns at once when *guard == 0.
+ * ss_i64_differs: flag_out = (a[0..count) != b[0..count)) -- lets the device decide whether a new edge tensor OBJECT also
+ * has new CONTENT, so a cached CSR (and everything memoised on it) is revalidated without a host round trip. */
+int ss_csr_build_nosync(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_rows, int64_t *rowptr,
+                        int32_t *colidx, int64_t *stats_out, void *workspace, int64_t workspace_bytes, const int32_t *guard,
+                        ss_stream_t stream);
+int ss_i64_differs(const int64_t *a, const int64_t *b, int64_t count, int32_t *flag_out, ss_stream_t stream);
 /* EXPERIMENTAL, opt-in (SS_B200_CSR_BIN=1 in the Python host), not on the default path, MEASURED SLOWER (profiles/r02_experiments_call_a.txt: 29.3 vs 22.5 ms): one streaming pass that groups
  * the edges by destination block (dst >> shift, at most 2048 blocks; capacities = differences of rowptr) into
  * src32_out / dst32_out so that the fill walks colidx window by window and completes its 32-byte sectors in L2.
@@ -197,12 +244,53 @@ int ss_khop_merge(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, 
  * (cuMulticast / symmetric memory `multicast_ptr`), addressed like rec_out / cards_out; when given, every
  * store is ONE `multimem.st` that the switch replicates into all GPUs' copies (the writer's included) and the
  * peer arrays are ignored.  P=128 / p=8 engines only. */
-#define SS_MAX_PEERS 7
 int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const void *rec_in,
                         int64_t in_rows, int64_t in_stride, void *rec_out, int64_t out_stride, int num_perm, int hll_p,
                         void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
                         const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
                         float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, ss_stream_t stream);
+
+/* Layout-general form of the merge (everything ss_khop_merge / ss_khop_merge_peers do, plus):
+ *   layout      what a row of rec_in / rec_out holds (P=128, p=8 engines, TMA variant):
+ *                 SS_LAYOUT_FULL     768 B  [128 x u32 MinHash | 256 x u8 HLL]        the hop tables
+ *                 SS_LAYOUT_MINHASH  512 B  [128 x u32 MinHash]                       MinhashPropagation called alone
+ *                 SS_LAYOUT_HLL      256 B  [256 x i8 registers]  = the reference's int8 [N, 256] tensor AS IS
+ *                                           (signed max, exact for any int8 content)  HllPropagation called alone
+ *                 SS_LAYOUT_HALF     384 B  [64 x u32 MinHash | 128 x u8 HLL]          one column half of a record
+ *               cards_out needs all 256 registers of a row: FULL and HLL only
+ *   peer_mask   device uint8 [n_rows] or NULL: bit i set = peer i reads output row r at some point (it owns a
+ *               destination with r as in-neighbour); rows whose bit is clear are not stored to that peer ("halo push":
+ *               on R-MAT-24 over 8 GPUs only ~30 % of the (row, peer) pairs are ever read).  Cards are always replicated.
+ *   guard       device int32 or NULL: when *guard == 0 at launch time the kernels return at once.  Lets a memoised
+ *               pipeline (ELPH re-propagating an unchanged graph every batch, models/elph.py:180-218) be re-enqueued
+ *               without a host synchronisation deciding whether the cached result is still valid. */
+#define SS_LAYOUT_FULL 0
+#define SS_LAYOUT_MINHASH 1
+#define SS_LAYOUT_HLL 2
+#define SS_LAYOUT_HALF 3
+typedef struct ss_merge_desc {
+    const int64_t *rowptr;
+    const int32_t *colidx;
+    int64_t n_rows, nnz;
+    const void *rec_in;
+    int64_t in_rows, in_stride;
+    void *rec_out;
+    int64_t out_stride;
+    int32_t num_perm, hll_p, layout, variant;
+    void *workspace;
+    int64_t workspace_bytes;
+    float *cards_out;
+    int64_t cards_stride;
+    const ss_hll_consts *hc;
+    int32_t n_peers, reserved;
+    void *const *peer_rec_out;
+    float *const *peer_cards_out;
+    const uint8_t *peer_mask;
+    void *mc_rec_out;
+    float *mc_cards_out;
+    const int32_t *guard;
+} ss_merge_desc;
+int ss_khop_merge_ex(const ss_merge_desc *desc, ss_stream_t stream);
 
 /* operator forms on the reference's own tensor layouts (ELPH calls these per batch,
  * /root/reference/src/models/elph.py:209-212): element-wise signed min (int64) / max (int8) over
@@ -212,6 +300,9 @@ int ss_prop_min_i64(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows
                     int64_t *out, int64_t width, ss_stream_t stream);
 int ss_prop_max_i8(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int8_t *x, int8_t *out,
                    int64_t width, ss_stream_t stream);
+/* ss_prop_min_i64 that returns at once when *guard == 0 (guard: device int32 or NULL; see ss_pack_records_ex) */
+int ss_prop_min_i64_guarded(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *x, int64_t *out,
+                            int64_t width, const int32_t *guard, ss_stream_t stream);
 
 /* ---- K3: HyperLogLog++ cardinality ---------------------------------------------------------------
  * Replaces ElphHashes.hll_count (hashing.py:212-232) with _linearcounting (:194-195),
@@ -246,6 +337,24 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
                      int num_perm, int hll_p, const float *cards, int64_t cards_stride,
                      const ss_hll_consts *hc, int flags, float *features_out, float *inter_out,
                      int32_t *error_flag, ss_stream_t stream);
+
+/* The same over NODE-SHARDED tables (multi-GPU): this rank's hop tables hold its own row block plus the halo
+ * rows it gathered while building (local_rows[x] != 0); every other record is read from its OWNER's copy, mapped into
+ * this process over NVLink (symmetric memory / CUDA IPC), so the last hop -- which no later hop gathers from -- is never
+ * replicated at all and hops 1..K-1 only where a neighbour list needed them.  All copies share the local row stride.
+ * shard == NULL or n_ranks == 1: exactly ss_link_features. */
+typedef struct ss_shard_view {
+    int32_t n_ranks, rank;
+    int32_t last_hop_own_only;                        /* 1: hop K is valid for the own row block only */
+    int32_t reserved;
+    int64_t bounds[SS_MAX_PEERS + 2];                 /* rank q owns rows [bounds[q], bounds[q+1]) */
+    const void *peer_records[4][SS_MAX_PEERS + 1];    /* [hop][rank] -> that rank's copy of the hop table (own entry ignored) */
+    const uint8_t *local_rows;                        /* device uint8 [num_rows]: 1 = hops 1..K-1 of the row are valid here */
+} ss_shard_view;
+int ss_link_features_sharded(const int64_t *links, int64_t n_links, const ss_hop_view *hops, int max_hops,
+                             int num_perm, int hll_p, const float *cards, int64_t cards_stride,
+                             const ss_hll_consts *hc, int flags, float *features_out, float *inter_out,
+                             int32_t *error_flag, const ss_shard_view *shard, ss_stream_t stream);
 
 /* ---- next row: common-neighbour heuristics on a SORTED CSR adjacency ------------
  * Replaces CN / AA / RA of /root/reference/src/heuristics.py:11-71 (scipy A[src].multiply(A_[dst]) row sums;

@@ -40,10 +40,14 @@ static CsrWorkspace carve(void *ws, int64_t n_rows) {
 // pass 1 over the COO list: in-degree histogram of the owned rows, max / min node id, and optional 32-bit device
 // copies of both endpoint arrays.  The loads are fully coalesced, so src / dst may live in pinned HOST memory and
 // are then consumed at PCIe rate with no staging copy (the 32-bit copies keep pass 2 off the bus).
+// kernels of a memoised pipeline take a GUARD (device int32 or NULL): they return at once when *guard == 0
+__device__ __forceinline__ bool csr_skip(const int *guard) { return guard && *reinterpret_cast<const volatile int *>(guard) == 0; }
+
 __global__ void __launch_bounds__(256) degree_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
                                                       int64_t n_edges, int64_t row_begin, int64_t n_rows, uint32_t *deg,
                                                       int32_t *__restrict__ src32, int32_t *__restrict__ dst32,
-                                                      long long *stats) {
+                                                      long long *stats, const int *guard = nullptr) {
+    if (csr_skip(guard)) return;
     long long mx = -1, mn = 0x7fffffffffffffffll;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t dv = dst[e];
@@ -96,8 +100,10 @@ __device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t *smem) {
 // phase 1: total of each tile of SCAN_TILE rows
 __global__ void __launch_bounds__(SCAN_BLOCK) tile_sum_kernel(const uint32_t *__restrict__ deg, int64_t n_rows,
                                                                int64_t row_begin, int64_t n_self_loops_arg,
-                                                               const long long *stats, int64_t *__restrict__ tile_sum) {
+                                                               const long long *stats, int64_t *__restrict__ tile_sum,
+                                                               const int *guard = nullptr) {
     __shared__ int64_t sm[SCAN_BLOCK / 32];
+    if (csr_skip(guard)) return;
     const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int64_t v = 0;
@@ -108,9 +114,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK) tile_sum_kernel(const uint32_t *__
 }
 
 // phase 2: one block turns the tile totals into exclusive offsets (serial over chunks of blockDim tiles)
-__global__ void __launch_bounds__(1024) tile_scan_kernel(int64_t *tile_sum, int64_t n_tiles) {
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int64_t *tile_sum, int64_t n_tiles, const int *guard = nullptr) {
     __shared__ int64_t warp_tot[32];
     __shared__ int64_t carry_s;
+    if (csr_skip(guard)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -150,8 +157,9 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int64_t *tile_sum, int6
 __global__ void __launch_bounds__(SCAN_BLOCK) rowptr_kernel(const uint32_t *__restrict__ deg, int64_t n_rows,
                                                              int64_t row_begin, int64_t n_self_loops_arg,
                                                              long long *stats, const int64_t *__restrict__ tile_off,
-                                                             int64_t *__restrict__ rowptr) {
+                                                             int64_t *__restrict__ rowptr, const int *guard = nullptr) {
     __shared__ int64_t warp_tot[SCAN_BLOCK / 32];
+    if (csr_skip(guard)) return;
     const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -189,7 +197,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) rowptr_kernel(const uint32_t *__re
 
 // fill cursors that already hold the absolute write position: cursor[r] = low 32 bits of rowptr[r]
 __global__ void __launch_bounds__(256) cursor_init_kernel(const int64_t *__restrict__ rowptr, int64_t n_rows,
-                                                           uint32_t *__restrict__ cursor) {
+                                                           uint32_t *__restrict__ cursor, const int *guard = nullptr) {
+    if (csr_skip(guard)) return;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
         cursor[r] = (uint32_t)rowptr[r];
 }
@@ -201,7 +210,9 @@ template <typename IdT, bool ABS_CURSOR>
 __global__ void __launch_bounds__(256) fill_kernel(const IdT *__restrict__ src, const IdT *__restrict__ dst,
                                                     int64_t n_edges, int64_t n_self_loops_arg, const long long *stats,
                                                     int64_t row_begin, int64_t n_rows, const int64_t *__restrict__ rowptr,
-                                                    uint32_t *cursor, int32_t *__restrict__ colidx) {
+                                                    uint32_t *cursor, int32_t *__restrict__ colidx,
+                                                    const int *guard = nullptr, int64_t clamp_cols = 0) {
+    if (csr_skip(guard)) return;
     const int64_t n_self_loops = resolve_loops(n_self_loops_arg, stats);
     const int64_t total = n_edges + n_rows;
     const bool fits32 = ABS_CURSOR && (uint64_t)__ldg(rowptr + n_rows) < (1ull << 32);
@@ -211,6 +222,9 @@ __global__ void __launch_bounds__(256) fill_kernel(const IdT *__restrict__ src, 
             d = (int64_t)dst[t] - row_begin;
             s = (int64_t)src[t];
             if (d < 0 || d >= n_rows) continue;
+            // deferred validation (sync-free callers): an out-of-range source must never become a gather index;
+            // the id statistics of the degree pass carry the error to the host
+            if (clamp_cols > 0 && (s < 0 || s >= clamp_cols)) s = 0;
         } else {
             d = t - n_edges;
             s = row_begin + d;
@@ -326,7 +340,9 @@ struct SortedArgs {
     const int64_t *key;
     const int64_t *val;
     int64_t n;              // edges in this chunk
-    int64_t e_base;         // global index of key[0]
+    int64_t e_base;         // index of key[0] in the whole list
+    int64_t e_origin;       // index (in the whole list) of the first edge of this CSR: positions are relative to it
+    int64_t row_begin;      // first row of this CSR (node-sharded builds); rows are [row_begin, row_begin + n_rows)
     int64_t n_rows;
     int64_t capacity;       // entries colidx can hold
     int loops;              // 1: implicit self loops (first in row)
@@ -337,47 +353,59 @@ struct SortedArgs {
     long long *carry;       // [2]: last key / last val of the previous chunk
 };
 
-__device__ __forceinline__ uint64_t fp_mix(uint64_t x) {  // murmur3 finaliser
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-    return x;
+// 32-bit keyed mixes (murmur3-style finalisers) of an ORDERED id pair; four independent 32-bit hashes per direction
+// would be overkill: two, accumulated into 64-bit sums, give a multiset fingerprint whose false-accept probability
+// is ~2^-46 per accumulator (sum of E random 32-bit values spreads over 2^32 sqrt(E) values) and ~2^-92 for the pair
+__device__ __forceinline__ uint32_t fp_mix_a(uint32_t x, uint32_t y, uint32_t key) {
+    uint32_t h = (x * 0x9e3779b1u) ^ y ^ key;
+    h ^= h >> 15; h *= 0x85ebca77u; h ^= h >> 13; h *= 0xc2b2ae3du; h ^= h >> 16;
+    return h;
 }
-__device__ __forceinline__ uint64_t fp_second(uint64_t h) {  // non-linear in h: a second, cheaper 64-bit check
-    return (uint64_t)((uint32_t)(h >> 32) | 1u) * (uint64_t)((uint32_t)h ^ 0x9e3779b9u) + (h >> 17);
+__device__ __forceinline__ uint32_t fp_mix_b(uint32_t x, uint32_t y, uint32_t key) {
+    uint32_t h = (y * 0x27d4eb2fu) + (x ^ key) * 0x165667b1u;
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
 }
 
 __global__ void __launch_bounds__(256) sorted_csr_kernel(const SortedArgs a) {
     const int lane = threadIdx.x & 31;
     unsigned long long fa = 0, fb = 0, ra = 0, rb = 0;
-    long long mx = -1, mn = 0x7fffffffffffffffll;
+    int mx = -1, mn = 0x7fffffff;
     unsigned bad_val = 0, bad_range = 0;
     bool dead = false;  // an order violation was seen (by this warp or any other): the result will be discarded
     unsigned long long *st = (unsigned long long *)a.stats;
+    const uint32_t ka = (uint32_t)a.ka, kb = (uint32_t)a.kb;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // whole warps iterate together (the tail is padded with inactive lanes) so that shuffles are well defined
     const int64_t n_pad = (a.n + 31) & ~(int64_t)31;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
         const bool live = i < a.n;
-        const int64_t k = live ? a.key[i] : 0;
-        const int64_t v = live ? a.val[i] : 0;
-        int64_t kp = __shfl_up_sync(FULL, k, 1);
-        int64_t vp = __shfl_up_sync(FULL, v, 1);
+        const int64_t k64 = live ? a.key[i] : 0;
+        const int64_t v64 = live ? a.val[i] : 0;
+        // ids outside [0, 2^31) are range errors; inside the loop everything is 32-bit (-2 marks an invalid id)
+        const bool id_ok = ((uint64_t)k64 | (uint64_t)v64) < (1ull << 31);
+        const int k = id_ok ? (int)k64 : -2, v = id_ok ? (int)v64 : -2;
+        int kp = __shfl_up_sync(FULL, k, 1);
+        int vp = __shfl_up_sync(FULL, v, 1);
         if (lane == 0) {
-            if (i > 0) { kp = a.key[i - 1]; vp = a.val[i - 1]; }
-            else if (a.e_base > 0) { kp = a.carry[0]; vp = a.carry[1]; }
-            else { kp = -1; vp = -1; }
+            if (i > 0) {
+                const int64_t a0 = a.key[i - 1], a1 = a.val[i - 1];
+                const bool okp = ((uint64_t)a0 | (uint64_t)a1) < (1ull << 31);
+                kp = okp ? (int)a0 : -2; vp = okp ? (int)a1 : -2;
+            } else if (a.e_base > a.e_origin) {
+                const int64_t a0 = a.carry[0], a1 = a.carry[1];
+                const bool okp = ((uint64_t)a0 | (uint64_t)a1) < (1ull << 31);
+                kp = okp ? (int)a0 : -2; vp = okp ? (int)a1 : -2;
+            } else { kp = (int)a.row_begin - 1; vp = -1; }
         }
-        const int64_t e = a.e_base + i;
-        bool ok = live;
+        const int64_t e = a.e_base + i - a.e_origin;   // position among the edges of this CSR
+        const int row_lo = (int)a.row_begin, row_hi = (int)(a.row_begin + a.n_rows);
+        bool ok = live && id_ok && k >= row_lo && k < row_hi && kp >= row_lo - 1;
         if (live) {
-            mx = max(mx, (long long)max(k, v));
-            mn = min(mn, (long long)min(k, v));
-            const uint64_t hf = fp_mix((((uint64_t)k << 32) | (uint64_t)(uint32_t)v) ^ a.ka);
-            const uint64_t hr = fp_mix((((uint64_t)v << 32) | (uint64_t)(uint32_t)k) ^ a.ka);
-            fa += hf; ra += hr;
-            fb += fp_second(hf ^ a.kb); rb += fp_second(hr ^ a.kb);
-            if (v < vp) bad_val = 1;   // (only meaningful for the caller's "is the OTHER row sorted" question)
-            if (k < 0 || k >= a.n_rows || (uint64_t)v >= (1ull << 31)) { bad_range = 1; ok = false; }
-            if (kp < -1 || kp >= a.n_rows) ok = false;
+            if (!id_ok || k < row_lo || k >= row_hi) bad_range = 1;
+            if (id_ok) { mx = max(mx, max(k, v)); mn = min(mn, min(k, v)); }
+            else { mn = min(mn, (k64 < 0 || v64 < 0) ? -1 : mn); mx = max(mx, (k64 >= (1ll << 31) || v64 >= (1ll << 31)) ? 0x7fffffff : mx); }
+            if (v < vp) bad_val = 1;   // (only meaningful for the caller's "is the OTHER row ordered" question)
         }
         // The pass is speculative.  On an unordered list the "rows that start here" ranges below are garbage and
         // could add up to E * n_rows writes, so all structural work stops as soon as ANY warp has seen a violation
@@ -386,35 +414,38 @@ __global__ void __launch_bounds__(256) sorted_csr_kernel(const SortedArgs a) {
         if (viol && !dead && lane == 0) atomicAdd(st + 8, 1ull);
         dead = dead || viol;
         if (!dead) dead = __any_sync(FULL, *(volatile unsigned long long *)(st + 8) != 0ull);
-        if (dead) {
-            if (live && i == a.n - 1) { a.carry[0] = k; a.carry[1] = v; }
-            continue;
+        if (live && i == a.n - 1) { a.carry[0] = k64; a.carry[1] = v64; }  // read by the next chunk (stream order)
+        if (dead) continue;
+        if (live) {
+            const uint32_t hf = fp_mix_a((uint32_t)k, (uint32_t)v, ka), hr = fp_mix_a((uint32_t)v, (uint32_t)k, ka);
+            fa += hf; ra += hr;
+            fb += fp_mix_b((uint32_t)k, (uint32_t)v, kb); rb += fp_mix_b((uint32_t)v, (uint32_t)k, kb);
         }
         // rows (kp, k] start at this edge.  Short gaps inline; long ones (runs of rows without edges) warp-wide
-        const int64_t gap = (ok && k > kp) ? (k - kp) : 0;
+        const int gap = (ok && k > kp) ? (k - kp) : 0;
         if (gap > 0 && gap <= 4) {
-            for (int64_t r = kp + 1; r <= k; ++r) {
-                const int64_t pos = e + (a.loops ? r : 0);
-                a.rowptr[r] = pos;
-                if (a.loops && pos < a.capacity) a.colidx[pos] = (int32_t)r;
+            for (int r = kp + 1; r <= k; ++r) {
+                const int64_t pos = e + (a.loops ? r - row_lo : 0);
+                a.rowptr[r - row_lo] = pos;
+                if (a.loops && pos < a.capacity) a.colidx[pos] = r;
             }
         }
         unsigned longs = __ballot_sync(FULL, gap > 4);
         while (longs) {
             const int b = __ffs(longs) - 1;
             longs &= longs - 1;
-            const int64_t r0 = __shfl_sync(FULL, kp, b) + 1, r1 = __shfl_sync(FULL, k, b), eb = __shfl_sync(FULL, e, b);
-            for (int64_t r = r0 + lane; r <= r1; r += 32) {
-                const int64_t pos = eb + (a.loops ? r : 0);
-                a.rowptr[r] = pos;
-                if (a.loops && pos < a.capacity) a.colidx[pos] = (int32_t)r;
+            const int r0 = __shfl_sync(FULL, kp, b) + 1, r1 = __shfl_sync(FULL, k, b);
+            const int64_t eb = a.e_base + (i - lane + b) - a.e_origin;
+            for (int r = r0 + lane; r <= r1; r += 32) {
+                const int64_t pos = eb + (a.loops ? r - row_lo : 0);
+                a.rowptr[r - row_lo] = pos;
+                if (a.loops && pos < a.capacity) a.colidx[pos] = r;
             }
         }
         if (ok) {
-            const int64_t pos = e + (a.loops ? k + 1 : 0);
-            if (pos < a.capacity) a.colidx[pos] = (int32_t)v;
+            const int64_t pos = e + (a.loops ? k - row_lo + 1 : 0);
+            if (pos < a.capacity) a.colidx[pos] = v;
         }
-        if (live && i == a.n - 1) { a.carry[0] = k; a.carry[1] = v; }  // read by the next chunk (stream order)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -424,32 +455,69 @@ __global__ void __launch_bounds__(256) sorted_csr_kernel(const SortedArgs a) {
     }
     bad_val = __any_sync(FULL, bad_val); bad_range = __any_sync(FULL, bad_range);
     if (lane == 0) {
-        if (mx >= 0) atomicMax(a.stats + 0, mx);
-        if (mn != 0x7fffffffffffffffll) atomicMin(a.stats + 3, mn);
+        if (mx >= 0) atomicMax(a.stats + 0, (long long)mx);
+        if (mn != 0x7fffffff) atomicMin(a.stats + 3, (long long)mn);
         atomicAdd(st + 4, fa); atomicAdd(st + 5, fb); atomicAdd(st + 6, ra); atomicAdd(st + 7, rb);
         if (bad_val) atomicAdd(st + 9, 1ull);
         if (bad_range) atomicAdd(st + 10, 1ull);
     }
 }
 
-// rows above the last key: r in (last, n_rows]: rowptr[r] = E + min(r, L), self loops of (last, L); nnz, loop count
-__global__ void __launch_bounds__(256) sorted_csr_finish_kernel(int64_t n_edges, int64_t n_rows, int64_t capacity, int loops,
-                                                                 int64_t *rowptr, int32_t *colidx, long long *stats,
+// rows above the last key of this CSR: r in (last, row_begin + n_rows]: rowptr = E + (self loops below r inside the
+// block), self loops of the rows below L = max id + 1; nnz and loop count into stats
+__global__ void __launch_bounds__(256) sorted_csr_finish_kernel(int64_t n_edges, int64_t row_begin, int64_t n_rows, int64_t capacity,
+                                                                 int loops, int64_t *rowptr, int32_t *colidx, long long *stats,
                                                                  const long long *carry) {
-    int64_t last = n_edges > 0 ? carry[0] : -1;
-    last = last < -1 ? -1 : (last > n_rows ? n_rows : last);
-    const int64_t L = loops ? (int64_t)stats[0] + 1 : 0;  // max id + 1
-    for (int64_t r = last + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows;
+    int64_t last = n_edges > 0 ? carry[0] : row_begin - 1;
+    last = last < row_begin - 1 ? row_begin - 1 : (last > row_begin + n_rows ? row_begin + n_rows : last);
+    const int64_t L = loops ? (int64_t)stats[0] + 1 : 0;  // max id + 1 (global)
+    auto loops_below = [&](int64_t r) {  // self loops of rows [row_begin, r)
+        int64_t x = (r < L ? r : L) - row_begin;
+        return x < 0 ? 0 : x;
+    };
+    for (int64_t r = last + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= row_begin + n_rows;
          r += (int64_t)gridDim.x * blockDim.x) {
-        if (r < 0) continue;
-        const int64_t pos = n_edges + (r < L ? r : L);
-        rowptr[r] = pos;
-        if (r < L && r < n_rows && pos < capacity) colidx[pos] = (int32_t)r;
+        const int64_t pos = n_edges + loops_below(r);
+        rowptr[r - row_begin] = pos;
+        if (r < L && r < row_begin + n_rows && pos < capacity) colidx[pos] = (int32_t)r;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        stats[1] = n_edges + (L < n_rows ? L : n_rows);  // nnz (only meaningful when max id < n_rows)
+        stats[1] = n_edges + loops_below(row_begin + n_rows);  // nnz (only meaningful when max id < number of nodes)
         stats[2] = L;
     }
+}
+
+// cost-balanced row blocks of a key-ordered list without a histogram: cost(r) = (#edges with key < r) + row_cost * r,
+// cut at the cumulative shares cum[q]; one thread per cut, nested binary searches (key may be a pinned host pointer)
+__global__ void sorted_bounds_kernel(const int64_t *__restrict__ key, int64_t n_edges, int64_t n_rows, double row_cost,
+                                     const double *__restrict__ cum, int n_cuts, int64_t *bounds, int64_t *edge_off) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    auto lower = [&](int64_t r) {  // first e with key[e] >= r
+        int64_t lo = 0, hi = n_edges;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (key[mid] < r) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    if (q == 0) { bounds[0] = 0; edge_off[0] = 0; bounds[n_cuts + 1] = n_rows; edge_off[n_cuts + 1] = n_edges; }
+    if (q >= n_cuts) return;
+    const double total = (double)n_edges + row_cost * (double)n_rows;
+    const double target = cum[q] * total;
+    int64_t lo = 0, hi = n_rows;  // smallest r with cost(r) >= target
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((double)lower(mid) + row_cost * (double)mid < target) lo = mid + 1; else hi = mid;
+    }
+    bounds[q + 1] = lo;
+    edge_off[q + 1] = lower(lo);
+}
+
+// mark[colidx[e]] = 1: the rows a rank's neighbour lists read (its halo + own rows), for the halo push of the
+// node-sharded build
+__global__ void __launch_bounds__(256) mark_rows_kernel(const int32_t *__restrict__ colidx, int64_t nnz, uint8_t *mark) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+        mark[__ldg(colidx + e)] = 1;
 }
 
 // SS_B200_CSR_FILL=legacy keeps zero-based cursors + a rowptr read per edge (the first version)
@@ -582,17 +650,28 @@ int ss_csr_bin_edges(const int64_t *src, const int64_t *dst, const int32_t *src3
 int ss_csr_sorted_chunk(const int64_t *key, const int64_t *val, int64_t n_edges, int64_t e_base, int64_t n_rows,
                         int add_self_loops, int64_t colidx_capacity, uint64_t fp_key_a, uint64_t fp_key_b, int64_t *rowptr,
                         int32_t *colidx, int64_t *stats_io, int64_t *carry_io, ss_stream_t stream) {
-    SS_REQUIRE(n_edges >= 0 && e_base >= 0 && n_rows >= 0 && colidx_capacity >= 0, "negative size passed to ss_csr_sorted_chunk");
+    return ss_csr_sorted_chunk_rows(key, val, n_edges, e_base, 0, 0, n_rows, add_self_loops, colidx_capacity, fp_key_a,
+                                    fp_key_b, rowptr, colidx, stats_io, carry_io, stream);
+}
+
+int ss_csr_sorted_chunk_rows(const int64_t *key, const int64_t *val, int64_t n_edges, int64_t e_base, int64_t e_origin,
+                             int64_t row_begin, int64_t n_rows, int add_self_loops, int64_t colidx_capacity,
+                             uint64_t fp_key_a, uint64_t fp_key_b, int64_t *rowptr, int32_t *colidx, int64_t *stats_io,
+                             int64_t *carry_io, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && e_base >= e_origin && e_origin >= 0 && row_begin >= 0 && n_rows >= 0 && colidx_capacity >= 0,
+               "bad sizes passed to ss_csr_sorted_chunk");
+    SS_REQUIRE(row_begin + n_rows < (1ll << 31), "node ids must be < 2^31");
     SS_REQUIRE(rowptr && colidx && stats_io && carry_io, "null pointer passed to ss_csr_sorted_chunk");
     SS_REQUIRE(n_edges == 0 || (key && val), "key/val is null");
     cudaStream_t st = (cudaStream_t)stream;
-    if (e_base == 0) {
+    if (e_base == e_origin) {
         const long long init[12] = {-1, 0, 0, 0x7fffffffffffffffll, 0, 0, 0, 0, 0, 0, 0, 0};
         SS_CUDA(cudaMemcpyAsync(stats_io, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     if (n_edges == 0) return SS_OK;
     ss::SortedArgs a;
-    a.key = key; a.val = val; a.n = n_edges; a.e_base = e_base; a.n_rows = n_rows; a.capacity = colidx_capacity;
+    a.key = key; a.val = val; a.n = n_edges; a.e_base = e_base; a.e_origin = e_origin; a.row_begin = row_begin;
+    a.n_rows = n_rows; a.capacity = colidx_capacity;
     a.loops = add_self_loops ? 1 : 0; a.ka = fp_key_a; a.kb = fp_key_b; a.rowptr = rowptr; a.colidx = colidx;
     a.stats = (long long *)stats_io; a.carry = (long long *)carry_io;
     int64_t blocks = (n_edges + 255) / 256;
@@ -604,19 +683,127 @@ int ss_csr_sorted_chunk(const int64_t *key, const int64_t *val, int64_t n_edges,
 
 int ss_csr_sorted_finish(int64_t n_edges_total, int64_t n_rows, int add_self_loops, int64_t colidx_capacity, int64_t *rowptr,
                          int32_t *colidx, int64_t *stats_io, const int64_t *carry, ss_stream_t stream) {
-    SS_REQUIRE(n_edges_total >= 0 && n_rows >= 0, "negative size passed to ss_csr_sorted_finish");
+    return ss_csr_sorted_finish_rows(n_edges_total, 0, n_rows, add_self_loops, colidx_capacity, rowptr, colidx, stats_io, carry,
+                                     stream);
+}
+
+int ss_csr_sorted_finish_rows(int64_t n_edges_total, int64_t row_begin, int64_t n_rows, int add_self_loops,
+                              int64_t colidx_capacity, int64_t *rowptr, int32_t *colidx, int64_t *stats_io,
+                              const int64_t *carry, ss_stream_t stream) {
+    SS_REQUIRE(n_edges_total >= 0 && n_rows >= 0 && row_begin >= 0, "negative size passed to ss_csr_sorted_finish");
     SS_REQUIRE(rowptr && colidx && stats_io && carry, "null pointer passed to ss_csr_sorted_finish");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_edges_total == 0) {
-        const long long init[12] = {-1, 0, 0, 0x7fffffffffffffffll, 0, 0, 0, 0, 0, 0, 0, 0};
-        SS_CUDA(cudaMemcpyAsync(stats_io, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    }
     int64_t blocks = (n_rows + 256) / 256;
     int64_t cap = (int64_t)ss::sm_count() * 8;
     ss::sorted_csr_finish_kernel<<<(int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap), 256, 0, st>>>(
-        n_edges_total, n_rows, colidx_capacity, add_self_loops ? 1 : 0, rowptr, colidx, (long long *)stats_io,
+        n_edges_total, row_begin, n_rows, colidx_capacity, add_self_loops ? 1 : 0, rowptr, colidx, (long long *)stats_io,
         (const long long *)carry);
     SS_LAUNCH_CHECK("sorted_csr_finish_kernel");
+    return SS_OK;
+}
+
+int ss_csr_sorted_bounds(const int64_t *key, int64_t n_edges, int64_t n_rows, double row_cost, const double *cum_shares,
+                         int n_cuts, int64_t *bounds_out, int64_t *edge_offsets_out, ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_cuts >= 0 && n_cuts <= SS_MAX_PEERS, "bad sizes passed to ss_csr_sorted_bounds");
+    SS_REQUIRE(bounds_out && edge_offsets_out && (n_cuts == 0 || cum_shares) && (n_edges == 0 || key),
+               "null pointer passed to ss_csr_sorted_bounds");
+    ss::sorted_bounds_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(key, n_edges, n_rows, row_cost, cum_shares, n_cuts, bounds_out,
+                                                               edge_offsets_out);
+    SS_LAUNCH_CHECK("sorted_bounds_kernel");
+    return SS_OK;
+}
+
+int ss_mark_rows(const int32_t *colidx, int64_t nnz, uint8_t *mark, ss_stream_t stream) {
+    SS_REQUIRE(nnz >= 0, "negative size passed to ss_mark_rows");
+    if (nnz == 0) return SS_OK;
+    SS_REQUIRE(colidx && mark, "null pointer passed to ss_mark_rows");
+    int64_t blocks = (nnz + 255) / 256;
+    int64_t cap = (int64_t)ss::sm_count() * 16;
+    ss::mark_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(colidx, nnz, mark);
+    SS_LAUNCH_CHECK("mark_rows_kernel");
+    return SS_OK;
+}
+
+// ---- synchronisation-free CSR of an edge list that already holds its self loops (operator forms) -------------------
+// What MinhashPropagation / HllPropagation get from ELPH.forward (models/elph.py:186: add_self_loops is applied by the
+// caller): nnz = n_edges is known to the host, so nothing has to be read back.  Ids are validated on the device:
+// stats_out = { max id, nnz of valid rows, 0, min id }, checked by the host whenever it next synchronises anyway; sources
+// outside [0, n_rows) are clamped to 0 and edges whose destination is outside are dropped, colidx is zero-filled first,
+// so a bad list can produce wrong sketches (the reference's CUDA scatter would hit a device-side assert) but never an
+// out-of-bounds access.  guard (device int32 or NULL): every kernel returns at once when *guard == 0 -- the caller
+// re-enqueues the build each time the edge tensor OBJECT changes and lets ss_i64_differs decide on the device whether
+// the content did.
+namespace ss {
+__global__ void __launch_bounds__(256) guarded_zero_kernel(uint32_t *p, int64_t n_words, long long *stats, const int *guard) {
+    if (csr_skip(guard)) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0u;
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[0] = -1; stats[1] = 0; stats[2] = 0; stats[3] = 0x7fffffffffffffffll;
+    }
+}
+
+__global__ void __launch_bounds__(256) i64_differs_kernel(const int64_t *__restrict__ a, const int64_t *__restrict__ b,
+                                                           int64_t n, int *flag) {
+    bool diff = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        diff |= (a[i] != b[i]);
+    if (__any_sync(FULL, diff) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+}  // namespace ss
+
+int ss_i64_differs(const int64_t *a, const int64_t *b, int64_t count, int32_t *flag_out, ss_stream_t stream) {
+    SS_REQUIRE(count >= 0 && flag_out, "bad arguments to ss_i64_differs");
+    cudaStream_t st = (cudaStream_t)stream;
+    SS_CUDA(cudaMemsetAsync(flag_out, 0, sizeof(int32_t), st));
+    if (count == 0) return SS_OK;
+    SS_REQUIRE(a && b, "null pointer passed to ss_i64_differs");
+    int64_t blocks = (count + 1023) / 1024;
+    int64_t cap = (int64_t)ss::sm_count() * 8;
+    ss::i64_differs_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a, b, count, flag_out);
+    SS_LAUNCH_CHECK("i64_differs_kernel");
+    return SS_OK;
+}
+
+int ss_csr_build_nosync(const int64_t *src, const int64_t *dst, int64_t n_edges, int64_t n_rows, int64_t *rowptr,
+                        int32_t *colidx, int64_t *stats_out, void *workspace, int64_t workspace_bytes, const int32_t *guard,
+                        ss_stream_t stream) {
+    SS_REQUIRE(n_edges >= 0 && n_rows >= 0, "negative size passed to ss_csr_build_nosync");
+    SS_REQUIRE(rowptr && stats_out && workspace && (n_edges == 0 || (src && dst && colidx)), "null pointer passed to ss_csr_build_nosync");
+    SS_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    if (workspace_bytes < ss::workspace_bytes(n_rows)) {
+        ss::set_error("csr workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)ss::workspace_bytes(n_rows));
+        return SS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    long long *stats = (long long *)stats_out;
+    ss::CsrWorkspace w = ss::carve(workspace, n_rows);
+    const int64_t cap = (int64_t)ss::sm_count() * 32;
+    auto grid_for = [&](int64_t items) { int64_t b = (items + 255) / 256; return (int)(b < cap ? (b < 1 ? 1 : b) : cap); };
+    ss::guarded_zero_kernel<<<grid_for(n_rows), 256, 0, st>>>(w.deg, n_rows, stats, guard);
+    SS_LAUNCH_CHECK("guarded_zero_kernel");
+    if (n_edges > 0) {
+        ss::guarded_zero_kernel<<<grid_for(n_edges), 256, 0, st>>>((uint32_t *)colidx, n_edges, nullptr, guard);
+        SS_LAUNCH_CHECK("guarded_zero_kernel");
+        ss::degree_kernel<<<grid_for(n_edges), 256, 0, st>>>(src, dst, n_edges, 0, n_rows, w.deg, nullptr, nullptr, stats, guard);
+        SS_LAUNCH_CHECK("degree_kernel");
+    }
+    if (n_rows == 0) {
+        SS_CUDA(cudaMemsetAsync(rowptr, 0, 8, st));
+        return SS_OK;
+    }
+    ss::tile_sum_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, 0, 0, stats, w.tile_sum, guard);
+    SS_LAUNCH_CHECK("tile_sum_kernel");
+    ss::tile_scan_kernel<<<1, 1024, 0, st>>>(w.tile_sum, w.n_tiles, guard);
+    SS_LAUNCH_CHECK("tile_scan_kernel");
+    ss::rowptr_kernel<<<(int)w.n_tiles, ss::SCAN_BLOCK, 0, st>>>(w.deg, n_rows, 0, 0, stats, w.tile_sum, rowptr, guard);
+    SS_LAUNCH_CHECK("rowptr_kernel");
+    ss::cursor_init_kernel<<<grid_for(n_rows), 256, 0, st>>>(rowptr, n_rows, w.deg, guard);
+    SS_LAUNCH_CHECK("cursor_init_kernel");
+    if (n_edges > 0) {
+        ss::fill_kernel<int64_t, true><<<grid_for(n_edges + n_rows), 256, 0, st>>>(src, dst, n_edges, 0, stats, 0, n_rows, rowptr,
+                                                                                w.deg, colidx, guard, n_rows);
+        SS_LAUNCH_CHECK("fill_kernel");
+    }
     return SS_OK;
 }
 

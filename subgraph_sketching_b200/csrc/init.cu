@@ -70,9 +70,15 @@ __global__ void __launch_bounds__(256) init_records_kernel(int64_t n, uint64_t f
 }
 
 // reference tensors -> records.  One thread per 8-byte unit.
+// error_flag (optional, int32[2] initialised to {0, 1} by the caller): [0] is set and [1] cleared when a value cannot be represented in a record (MinHash outside [0, 2^32), register
+// outside [0, 127]) -- the host then knows, without having synchronised up front, that the record engine was not
+// applicable to this tensor.  guard: see ss_khop_merge_ex.
 __global__ void __launch_bounds__(256) pack_kernel(const int64_t *__restrict__ mh, const int8_t *__restrict__ hll,
                                                     int64_t n, RecordShape s, uint8_t *__restrict__ out,
-                                                    int64_t out_stride) {
+                                                    int64_t out_stride, int *error_flag = nullptr,
+                                                    const int *guard = nullptr) {
+    if (guard && *reinterpret_cast<const volatile int *>(guard) == 0) return;
+    bool bad = false;
     const int64_t total = n * (int64_t)s.units;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = t / s.units;
@@ -81,19 +87,28 @@ __global__ void __launch_bounds__(256) pack_kernel(const int64_t *__restrict__ m
         if (u < s.mh_units) {
             if (!mh) continue;
             int j = 2 * u;
-            v.x = (j < s.P) ? (uint32_t)mh[i * s.P + j] : 0u;
-            v.y = (j + 1 < s.P) ? (uint32_t)mh[i * s.P + j + 1] : 0u;
+            const int64_t x = (j < s.P) ? mh[i * s.P + j] : 0, y = (j + 1 < s.P) ? mh[i * s.P + j + 1] : 0;
+            bad |= ((uint64_t)x | (uint64_t)y) >> 32 != 0;
+            v.x = (uint32_t)x;
+            v.y = (uint32_t)y;
         } else {
             if (!hll) continue;
             v = *reinterpret_cast<const uint2 *>(hll + i * (int64_t)s.m + (int64_t)(u - s.mh_units) * 8);
+            bad |= ((v.x | v.y) & 0x80808080u) != 0u;
         }
         *reinterpret_cast<uint2 *>(out + i * out_stride + (int64_t)u * 8) = v;
+    }
+    if (error_flag && bad) {  // int32[2]: [0] = 'does not fit' (set), [1] = 'fits' (cleared) -- either can serve as a guard
+        atomicExch(error_flag, 1);
+        atomicExch(error_flag + 1, 0);
     }
 }
 
 __global__ void __launch_bounds__(256) unpack_kernel(const uint8_t *__restrict__ rec, int64_t rec_stride, int64_t n,
                                                       RecordShape s,
-                                                      int64_t *__restrict__ mh, int8_t *__restrict__ hll) {
+                                                      int64_t *__restrict__ mh, int8_t *__restrict__ hll,
+                                                      const int *guard = nullptr) {
+    if (guard && *reinterpret_cast<const volatile int *>(guard) == 0) return;
     const int64_t total = n * (int64_t)s.units;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = t / s.units;
@@ -142,6 +157,11 @@ int ss_init_records(int64_t n, int64_t first_id, int num_perm, int hll_p, const 
 
 int ss_pack_records(const int64_t *minhash, const int8_t *hll, int64_t n, int num_perm, int hll_p, void *rec_out,
                     int64_t out_stride, ss_stream_t stream) {
+    return ss_pack_records_ex(minhash, hll, n, num_perm, hll_p, rec_out, out_stride, nullptr, nullptr, stream);
+}
+
+int ss_pack_records_ex(const int64_t *minhash, const int8_t *hll, int64_t n, int num_perm, int hll_p, void *rec_out,
+                       int64_t out_stride, int32_t *error_flag, const int32_t *guard, ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n >= 0, "n must be >= 0");
@@ -149,24 +169,30 @@ int ss_pack_records(const int64_t *minhash, const int8_t *hll, int64_t n, int nu
     SS_REQUIRE(rec_out && (minhash || hll), "null pointer passed to ss_pack_records");
     SS_REQUIRE(((uintptr_t)rec_out & 15) == 0, "record table must be 16-byte aligned");
     SS_REQUIRE(((uintptr_t)hll & 7) == 0, "hll tensor must be 8-byte aligned");
-    SS_REQUIRE(out_stride >= s.bytes && (out_stride & 15) == 0, "bad record stride %lld", (long long)out_stride);
+    // a MinHash-only table (hll == NULL) may be as narrow as the MinHash part of a record (SS_LAYOUT_MINHASH rows)
+    SS_REQUIRE(out_stride >= (hll ? s.bytes : s.mh_bytes) && (out_stride & 15) == 0, "bad record stride %lld", (long long)out_stride);
     int grid = ss::grid_for(n * s.units, 256);
-    ss::pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(minhash, hll, n, s, (uint8_t *)rec_out, out_stride);
+    ss::pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(minhash, hll, n, s, (uint8_t *)rec_out, out_stride, error_flag, guard);
     SS_LAUNCH_CHECK("pack_kernel");
     return SS_OK;
 }
 
 int ss_unpack_records(const void *rec, int64_t rec_stride, int64_t n, int num_perm, int hll_p, int64_t *minhash_out,
                       int8_t *hll_out, ss_stream_t stream) {
+    return ss_unpack_records_ex(rec, rec_stride, n, num_perm, hll_p, minhash_out, hll_out, nullptr, stream);
+}
+
+int ss_unpack_records_ex(const void *rec, int64_t rec_stride, int64_t n, int num_perm, int hll_p, int64_t *minhash_out,
+                         int8_t *hll_out, const int32_t *guard, ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n >= 0, "n must be >= 0");
     if (n == 0) return SS_OK;
     SS_REQUIRE(rec && (minhash_out || hll_out), "null pointer passed to ss_unpack_records");
     SS_REQUIRE(((uintptr_t)hll_out & 7) == 0, "hll tensor must be 8-byte aligned");
-    SS_REQUIRE(rec_stride >= s.bytes && (rec_stride & 15) == 0, "bad record stride %lld", (long long)rec_stride);
+    SS_REQUIRE(rec_stride >= (hll_out ? s.bytes : s.mh_bytes) && (rec_stride & 15) == 0, "bad record stride %lld", (long long)rec_stride);
     int grid = ss::grid_for(n * s.units, 256);
-    ss::unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)rec, rec_stride, n, s, minhash_out, hll_out);
+    ss::unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)rec, rec_stride, n, s, minhash_out, hll_out, guard);
     SS_LAUNCH_CHECK("unpack_kernel");
     return SS_OK;
 }

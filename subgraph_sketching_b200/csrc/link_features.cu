@@ -29,6 +29,12 @@ struct LinkArgs {
     RecordShape s;
     int64_t n_nodes;  // rows of the smallest hop table: link endpoints must be in [0, n_nodes)
     int *err;         // set to 1 if any endpoint is out of range (such links are evaluated on node 0)
+    // node-sharded tables (multi-GPU, batched kernel only): this rank's copies hold its own row block plus the
+    // halo rows it gathered during the build; any other row is read from its OWNER's copy over NVLink
+    int n_ranks, rank, last_hop_own_only;
+    int64_t bounds[SS_MAX_PEERS + 2];
+    const uint8_t *peer_hop[4][SS_MAX_PEERS + 1];
+    const uint8_t *local_rows;
 };
 
 // bounds check of a link endpoint (the reference would raise IndexError from torch indexing)
@@ -325,10 +331,25 @@ __device__ __forceinline__ int lk_select3(int idx, int a0, int a1, int a2) { ret
 __device__ __forceinline__ void lk_cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void lk_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void lk_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// which rank owns row `node` (row blocks are contiguous: bounds[q] <= node < bounds[q + 1])
+__device__ __forceinline__ int lk_owner(const LinkArgs &a, int node) {
+    int o = 0;
+    for (int q = 1; q < a.n_ranks; ++q) o += ((int64_t)node >= a.bounds[q]) ? 1 : 0;
+    return o;
+}
+// base pointer of the copy of hop table k1 (1-based) that holds a valid record of a node owned by `owner`;
+// `have` = this rank's copy of the replicated-by-halo hops holds the row
+__device__ __forceinline__ const uint8_t *lk_table(const LinkArgs &a, int k1, int K, int owner, bool have) {
+    if (a.n_ranks <= 1 || owner == a.rank) return a.hop[k1];
+    if (have && !(k1 == K && a.last_hop_own_only)) return a.hop[k1];
+    return a.peer_hop[k1][owner];
+}
+
 template <int K>
-__global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const LinkArgs a, const int tile) {
+__global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const LinkArgs a, const int tile, const int prefetch) {
     constexpr int C = K * K;
     constexpr int B = 32 / C;
     constexpr int F = K * (K + 2);
@@ -381,12 +402,32 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
             for (int j = 0; j < nb; ++j) {
                 const int2 e = reinterpret_cast<const int2 *>(ids + b0 + j)[0];  // broadcast read
                 const int u = e.x, v = e.y;
+                // pull the NEXT link's records into L2 while this one is evaluated (costs no registers): a warp has one
+                // link in flight, so without this every link pays a full DRAM round trip before its first instruction
+                if (prefetch && a.n_ranks <= 1 && b0 + j + 1 < cnt) {
+                    const int2 en = reinterpret_cast<const int2 *>(ids + b0 + j + 1)[0];
+#pragma unroll
+                    for (int x0 = 0; x0 < 12 * K; x0 += 32) {
+                        const int x = x0 + lane;
+                        const int rec = x / 6, line = x - rec * 6;       // 6 x 128-byte lines per record
+                        const int side = rec / K, k = rec - side * K;    // records 0..K-1: u, K..2K-1: v
+                        const int node = side ? en.y : en.x;
+                        if (x < 12 * K && (side || node != u)) {
+                            const uint8_t *base = k == 0 ? a.hop[1] : (k == 1 ? a.hop[2] : a.hop[3]);
+                            const int64_t strd = k == 0 ? a.stride[1] : (k == 1 ? a.stride[2] : a.stride[3]);
+                            lk_prefetch_l2(base + (int64_t)node * strd + line * 128);
+                        }
+                    }
+                }
+                const bool sharded = a.n_ranks > 1;
                 if (u != u_cur) {  // warp-uniform: a run of links with the same source keeps u's prepared records
                     u_cur = u;
                     big_u = 0;
+                    const int ow = sharded ? lk_owner(a, u) : 0;
+                    const bool have = sharded ? (__ldg(a.local_rows + u) != 0) : true;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const uint8_t *ru = a.hop[k + 1] + (int64_t)u * a.stride[k + 1];
+                        const uint8_t *ru = lk_table(a, k + 1, K, ow, have) + (int64_t)u * a.stride[k + 1];
                         const uint4 m = ld_nc_u4(ru + lane * 16);
                         const uint2 h = ld_nc_u2(ru + REC_MH + lane * 8);
                         prep_row_b(U[k], m, h, big_u);
@@ -394,9 +435,11 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
                 }
                 RowRegsB V[K];
                 uint32_t big = big_u;
+                const int ow_v = sharded ? lk_owner(a, v) : 0;
+                const bool have_v = sharded ? (__ldg(a.local_rows + v) != 0) : true;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const uint8_t *rv = a.hop[k + 1] + (int64_t)v * a.stride[k + 1];
+                    const uint8_t *rv = lk_table(a, k + 1, K, ow_v, have_v) + (int64_t)v * a.stride[k + 1];
                     const uint4 m = ld_nc_u4(rv + lane * 16);
                     const uint2 h = ld_nc_u2(rv + REC_MH + lane * 8);
                     prep_row_b(V[k], m, h, big);
@@ -766,7 +809,9 @@ static int launch_links(const LinkArgs &a, const int64_t *hop_rows, bool fast, c
         const int64_t n_tiles = (a.n_links + tile - 1) / tile;
         int64_t bl = (n_tiles + 7) / 8;
         int64_t cap_b = (int64_t)sm_count() * 3;
-        link_features_batched_kernel<K><<<(int)(bl < cap_b ? bl : cap_b), 256, 0, st>>>(a, (int)tile);
+        int prefetch = 1;
+        if (const char *e = getenv("SS_B200_LINK_PREFETCH")) prefetch = atoi(e);  // tuning knob
+        link_features_batched_kernel<K><<<(int)(bl < cap_b ? bl : cap_b), 256, 0, st>>>(a, (int)tile, prefetch);
         SS_LAUNCH_CHECK("link_features_batched_kernel");
     } else {
         link_features_generic_kernel<K><<<grid, 256, 0, st>>>(a);
@@ -782,6 +827,14 @@ extern "C" {
 int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *hops, int max_hops, int num_perm,
                      int hll_p, const float *cards, int64_t cards_stride, const ss_hll_consts *hc, int flags,
                      float *features_out, float *inter_out, int32_t *error_flag, ss_stream_t stream) {
+    return ss_link_features_sharded(links, n_links, hops, max_hops, num_perm, hll_p, cards, cards_stride, hc, flags,
+                                    features_out, inter_out, error_flag, nullptr, stream);
+}
+
+int ss_link_features_sharded(const int64_t *links, int64_t n_links, const ss_hop_view *hops, int max_hops, int num_perm,
+                             int hll_p, const float *cards, int64_t cards_stride, const ss_hll_consts *hc, int flags,
+                             float *features_out, float *inter_out, int32_t *error_flag, const ss_shard_view *shard,
+                             ss_stream_t stream) {
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(max_hops >= 1 && max_hops <= 3, "Only 1, 2 and 3 hop hashes are implemented (got %d)", max_hops);
@@ -818,6 +871,25 @@ int ss_link_features(const int64_t *links, int64_t n_links, const ss_hop_view *h
     for (int k = 2; k <= max_hops; ++k)
         if (hop_rows[k] < a.n_nodes) a.n_nodes = hop_rows[k];
     const bool fast = (num_perm == 128 && hll_p == 8);
+    a.n_ranks = 1;
+    if (shard && shard->n_ranks > 1) {
+        SS_REQUIRE(fast, "sharded tables need num_perm=128, hll_p=8");
+        SS_REQUIRE(shard->n_ranks <= SS_MAX_PEERS + 1 && shard->rank >= 0 && shard->rank < shard->n_ranks,
+                   "bad rank / world size in ss_shard_view");
+        SS_REQUIRE(shard->local_rows, "ss_shard_view.local_rows is null");
+        SS_REQUIRE(!ss::want_per_link_kernel() && !ss::want_tma_links(), "sharded tables are read by the batched kernel only");
+        a.n_ranks = shard->n_ranks;
+        a.rank = shard->rank;
+        a.last_hop_own_only = shard->last_hop_own_only;
+        a.local_rows = shard->local_rows;
+        for (int q = 0; q <= shard->n_ranks; ++q) a.bounds[q] = shard->bounds[q];
+        SS_REQUIRE(a.bounds[0] == 0 && a.bounds[shard->n_ranks] <= a.n_nodes, "row blocks must start at 0 and end within the tables");
+        for (int k = 1; k <= max_hops; ++k)
+            for (int q = 0; q < shard->n_ranks; ++q) {
+                a.peer_hop[k][q] = q == shard->rank ? a.hop[k] : (const uint8_t *)shard->peer_records[k][q];
+                SS_REQUIRE(a.peer_hop[k][q] && ((uintptr_t)a.peer_hop[k][q] & 15) == 0, "peer table of hop %d / rank %d is null or misaligned", k, q);
+            }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     switch (max_hops) {
         case 1: return ss::launch_links<1>(a, hop_rows, fast, st);

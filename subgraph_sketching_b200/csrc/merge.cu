@@ -58,6 +58,11 @@ struct MergeArgs {
     // NVSwitch multicast alternative: ONE multimem.st per store lands in every GPU's copy (own copy included)
     uint8_t *mc_out;
     float *mc_cards;
+    // halo push (optional): bit p of peer_mask[row] says whether peer p ever reads output row `row` (it owns a
+    // destination with that row as in-neighbour, or a link endpoint); rows nobody else reads stay local
+    const uint8_t *peer_mask;
+    // memoised pipelines: skip the launch when *guard == 0 (see guarded_skip)
+    const int *guard;
 };
 
 // HLL++ estimate of a row held as 8 registers per lane.  Not inlined: it is called once per output row
@@ -94,29 +99,152 @@ __device__ __forceinline__ void mc_st_f32(float *p, float v) {
     asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// ---- row layouts ---------------------------------------------------------------------------------------
+// What one row of the gathered table holds; a lane owns MW MinHash words and HW HLL words of it:
+//   FULL (768 B)  128 x u32 MinHash + 256 x u8 registers   lane: 16 B + 8 B   the hop tables of build_hash_tables
+//   MH   (512 B)  128 x u32 MinHash                        lane: 16 B         MinhashPropagation called singly
+//   HLL  (256 B)  256 x u8 registers                       lane:        8 B   HllPropagation called singly: the
+//                                                                             reference's int8 [N, 256] tensor AS IS
+//   HALF (384 B)  64 x u32 MinHash + 128 x u8 registers    lane:  8 B + 4 B   one column half of a record
+//                                                                             (column-sharded multi-GPU variants)
+constexpr int LAY_FULL = 0, LAY_MH = 1, LAY_HLL = 2, LAY_HALF = 3;
+template <int MODE> struct Lay;
+template <int MW_, int HW_, uint32_t BIAS_> struct LayBase {
+    static constexpr int MW = MW_, HW = HW_;
+    static constexpr int MH_BYTES = MW_ * 128, BYTES = (MW_ + HW_) * 128;
+    static constexpr uint32_t BIAS = BIAS_;  // see acc_merge
+};
+template <> struct Lay<LAY_FULL> : LayBase<4, 2, 0u> {};
+template <> struct Lay<LAY_MH> : LayBase<4, 0, 0u> {};
+template <> struct Lay<LAY_HLL> : LayBase<0, 2, 0x80808080u> {};
+template <> struct Lay<LAY_HALF> : LayBase<2, 1, 0u> {};
+
+// state of the row currently being reduced by a warp.  Positions are relative to the range start s
+// (32-bit: one compare per neighbour), clamped so that "started before" / "continues after" stay visible.
+// HLL registers are accumulated in two planes (even / odd bytes, each in its own 16-bit lane) so that the
+// register-wise max is the native 16x2 max (VIMNMX.U16x2 / VIMNMX3) -- a 4 x uint8 max does not exist in
+// hardware and costs 7 instructions when emulated.
+template <int MODE>
+struct RowStateT {
+    uint32_t mh[Lay<MODE>::MW > 0 ? Lay<MODE>::MW : 1];
+    uint32_t he[Lay<MODE>::HW > 0 ? Lay<MODE>::HW : 1], ho[Lay<MODE>::HW > 0 ? Lay<MODE>::HW : 1];
+    int cur;        // row index
+    int rs, re;     // neighbour range of the row relative to s: rs = -1 if it started before the range
+    int re_next;    // relative end of row cur + 1 (prefetched)
+};
+// one gathered (or finished) row as a lane sees it
+template <int MODE>
+struct RowVec {
+    uint32_t m[Lay<MODE>::MW > 0 ? Lay<MODE>::MW : 1];
+    uint32_t h[Lay<MODE>::HW > 0 ? Lay<MODE>::HW : 1];
+};
+constexpr int REL_CAP = 1 << 30;
+constexpr uint32_t EVEN = 0x00ff00ffu, ODD = 0xff00ff00u;
+
+__device__ __forceinline__ int rel_pos(int64_t abs_pos, int64_t s) {
+    const int64_t d = abs_pos - s;
+    return d < 0 ? -1 : (d > REL_CAP ? REL_CAP : (int)d);
+}
+template <int MODE>
+__device__ __forceinline__ void acc_reset(RowStateT<MODE> &st) {
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::MW; ++i) st.mh[i] = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::HW; ++i) { st.he[i] = 0u; st.ho[i] = 0u; }
+}
+// The HLL-only layout runs on the reference's int8 tensor as it is, and HllPropagation is a SIGNED max there
+// (hashing.py:38-45): bytes are biased by 0x80 inside the accumulator (signed order == unsigned order of x ^ 0x80;
+// the XOR folds into the plane-extracting LOP3), so any int8 content is merged exactly.  Records hold registers
+// in [0, 64] and need no bias.
+
+template <int MODE>
+__device__ __forceinline__ void acc_merge(RowStateT<MODE> &st, const RowVec<MODE> &r) {
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::MW; ++i) st.mh[i] = min(st.mh[i], r.m[i]);
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::HW; ++i) {
+        st.he[i] = __vmaxu2(st.he[i], (r.h[i] ^ Lay<MODE>::BIAS) & EVEN);
+        st.ho[i] = __vmaxu2(st.ho[i], (r.h[i] ^ Lay<MODE>::BIAS) & ODD);
+    }
+}
+// two neighbour rows at once: three-input min / max (VIMNMX3)
+template <int MODE>
+__device__ __forceinline__ void acc_merge2(RowStateT<MODE> &st, const RowVec<MODE> &r1, const RowVec<MODE> &r2) {
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::MW; ++i) st.mh[i] = __vimin3_u32(st.mh[i], r1.m[i], r2.m[i]);
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::HW; ++i) {
+        st.he[i] = __vimax3_u16x2(st.he[i], (r1.h[i] ^ Lay<MODE>::BIAS) & EVEN, (r2.h[i] ^ Lay<MODE>::BIAS) & EVEN);
+        st.ho[i] = __vimax3_u16x2(st.ho[i], (r1.h[i] ^ Lay<MODE>::BIAS) & ODD, (r2.h[i] ^ Lay<MODE>::BIAS) & ODD);
+    }
+}
+template <int MODE>
+__device__ __forceinline__ RowVec<MODE> acc_row(const RowStateT<MODE> &st) {
+    RowVec<MODE> r;
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::MW; ++i) r.m[i] = st.mh[i];
+#pragma unroll
+    for (int i = 0; i < Lay<MODE>::HW; ++i) r.h[i] = (st.he[i] | st.ho[i]) ^ Lay<MODE>::BIAS;
+    return r;
+}
+
+// vector accesses of a lane's slice of a row: MinHash words at lane * 4 MW, HLL words at mh_bytes + lane * 4 HW
+template <int W>
+__device__ __forceinline__ void ldg_words(const uint8_t *p, uint32_t *w) {
+    if (W == 4) { const uint4 v = ld_nc_u4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    if (W == 2) { const uint2 v = ld_nc_u2(p); w[0] = v.x; w[1] = v.y; }
+    if (W == 1) { w[0] = __ldg(reinterpret_cast<const uint32_t *>(p)); }
+}
+template <int W>
+__device__ __forceinline__ void stg_words(uint8_t *p, const uint32_t *w) {
+    if (W == 4) st_na_u4(p, make_uint4(w[0], w[1], w[2], w[3]));
+    if (W == 2) st_na_u2(p, make_uint2(w[0], w[1]));
+    if (W == 1) *reinterpret_cast<uint32_t *>(p) = w[0];
+}
+template <int W>
+__device__ __forceinline__ void mc_words(uint8_t *p, const uint32_t *w) {
+    if (W == 4) mc_st_u4(p, make_uint4(w[0], w[1], w[2], w[3]));
+    if (W == 2) mc_st_u2(p, make_uint2(w[0], w[1]));
+    if (W == 1) mc_st_f32(reinterpret_cast<float *>(p), __uint_as_float(w[0]));
+}
+template <int MODE>
+__device__ __forceinline__ RowVec<MODE> ldg_row(const uint8_t *row, int lane) {
+    RowVec<MODE> r;
+    ldg_words<Lay<MODE>::MW>(row + lane * (4 * Lay<MODE>::MW), r.m);
+    ldg_words<Lay<MODE>::HW>(row + Lay<MODE>::MH_BYTES + lane * (4 * Lay<MODE>::HW), r.h);
+    return r;
+}
+template <int MODE>
+__device__ __forceinline__ void stg_row(uint8_t *row, const RowVec<MODE> &r, int lane) {
+    stg_words<Lay<MODE>::MW>(row + lane * (4 * Lay<MODE>::MW), r.m);
+    stg_words<Lay<MODE>::HW>(row + Lay<MODE>::MH_BYTES + lane * (4 * Lay<MODE>::HW), r.h);
+}
+
 // final store of output row `row`: local table, its cardinality, and the same to every peer table
 // (one store per peer over NVLink, or one multicast store that the NVSwitch replicates to every GPU)
-__device__ __forceinline__ void store_row(const MergeArgs &a, int64_t row, const uint4 &mh, const uint2 &hl, int lane) {
+template <int MODE>
+__device__ __forceinline__ void store_row(const MergeArgs &a, int64_t row, const RowVec<MODE> &r, int lane) {
     const int64_t off = row * a.out_stride;
     if (a.mc_out) {
-        mc_st_u4(a.mc_out + off + lane * 16, mh);
-        mc_st_u2(a.mc_out + off + REC_MH + lane * 8, hl);
+        mc_words<Lay<MODE>::MW>(a.mc_out + off + lane * (4 * Lay<MODE>::MW), r.m);
+        mc_words<Lay<MODE>::HW>(a.mc_out + off + Lay<MODE>::MH_BYTES + lane * (4 * Lay<MODE>::HW), r.h);
     } else {
-        st_na_u4(a.out + off + lane * 16, mh);
-        st_na_u2(a.out + off + REC_MH + lane * 8, hl);
+        stg_row<MODE>(a.out + off, r, lane);
         for (int p = 0; p < a.n_peers; ++p) {
-            st_na_u4(a.peer_out[p] + off + lane * 16, mh);
-            st_na_u2(a.peer_out[p] + off + REC_MH + lane * 8, hl);
+            if (a.peer_mask && !((__ldg(a.peer_mask + row) >> p) & 1)) continue;  // halo push: peer p never reads this row
+            stg_row<MODE>(a.peer_out[p] + off, r, lane);
         }
     }
-    if (a.cards) {
-        float c = ROW_CARD(a, hl);
-        if (lane == 0) {
-            if (a.mc_cards) {
-                mc_st_f32(a.mc_cards + row * a.cards_stride, c);
-            } else {
-                a.cards[row * a.cards_stride] = c;
-                for (int p = 0; p < a.n_peers; ++p) a.peer_cards[p][row * a.cards_stride] = c;
+    if (MODE == LAY_FULL || MODE == LAY_HLL) {
+        if (a.cards) {
+            float c = ROW_CARD(a, make_uint2(r.h[0], r.h[Lay<MODE>::HW > 1 ? 1 : 0]));
+            if (lane == 0) {
+                if (a.mc_cards) {
+                    mc_st_f32(a.mc_cards + row * a.cards_stride, c);
+                } else {
+                    a.cards[row * a.cards_stride] = c;
+                    for (int p = 0; p < a.n_peers; ++p) a.peer_cards[p][row * a.cards_stride] = c;
+                }
             }
         }
     }
@@ -132,89 +260,49 @@ __device__ __forceinline__ int64_t row_of_position(const int64_t *__restrict__ r
     return lo;
 }
 
-// state of the row currently being reduced by a warp.  Positions are relative to the range start s
-// (32-bit: one compare per neighbour), clamped so that "started before" / "continues after" stay visible.
-// HLL registers are accumulated in two planes (even / odd bytes, each in its own 16-bit lane) so that the
-// register-wise max is the native 16x2 max (VIMNMX.U16x2 / VIMNMX3) -- a 4 x uint8 max does not exist in
-// hardware and costs 7 instructions when emulated.
-struct RowState {
-    uint4 mh;
-    uint2 he, ho;   // even / odd byte planes of the 8 HLL registers of this lane
-    int cur;        // row index
-    int rs, re;     // neighbour range of the row relative to s: rs = -1 if it started before the range
-    int re_next;    // relative end of row cur + 1 (prefetched)
-};
-constexpr int REL_CAP = 1 << 30;
-constexpr uint32_t EVEN = 0x00ff00ffu, ODD = 0xff00ff00u;
-
-__device__ __forceinline__ int rel_pos(int64_t abs_pos, int64_t s) {
-    const int64_t d = abs_pos - s;
-    return d < 0 ? -1 : (d > REL_CAP ? REL_CAP : (int)d);
-}
-__device__ __forceinline__ void acc_reset(RowState &st) {
-    st.mh = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    st.he = make_uint2(0u, 0u);
-    st.ho = make_uint2(0u, 0u);
-}
-__device__ __forceinline__ void acc_merge(RowState &st, const uint4 &m, const uint2 &h) {
-    st.mh.x = min(st.mh.x, m.x);
-    st.mh.y = min(st.mh.y, m.y);
-    st.mh.z = min(st.mh.z, m.z);
-    st.mh.w = min(st.mh.w, m.w);
-    st.he.x = __vmaxu2(st.he.x, h.x & EVEN);
-    st.he.y = __vmaxu2(st.he.y, h.y & EVEN);
-    st.ho.x = __vmaxu2(st.ho.x, h.x & ODD);
-    st.ho.y = __vmaxu2(st.ho.y, h.y & ODD);
-}
-// two neighbour rows at once: three-input min / max (VIMNMX3)
-__device__ __forceinline__ void acc_merge2(RowState &st, const uint4 &m1, const uint2 &h1, const uint4 &m2,
-                                           const uint2 &h2) {
-    st.mh.x = __vimin3_u32(st.mh.x, m1.x, m2.x);
-    st.mh.y = __vimin3_u32(st.mh.y, m1.y, m2.y);
-    st.mh.z = __vimin3_u32(st.mh.z, m1.z, m2.z);
-    st.mh.w = __vimin3_u32(st.mh.w, m1.w, m2.w);
-    st.he.x = __vimax3_u16x2(st.he.x, h1.x & EVEN, h2.x & EVEN);
-    st.he.y = __vimax3_u16x2(st.he.y, h1.y & EVEN, h2.y & EVEN);
-    st.ho.x = __vimax3_u16x2(st.ho.x, h1.x & ODD, h2.x & ODD);
-    st.ho.y = __vimax3_u16x2(st.ho.y, h1.y & ODD, h2.y & ODD);
-}
-__device__ __forceinline__ uint2 acc_hll(const RowState &st) { return make_uint2(st.he.x | st.ho.x, st.he.y | st.ho.y); }
-
 // write the finished (or partial) current row; n_pos = length of the range, w = range index
-__device__ __forceinline__ void flush_row(const MergeArgs &a, const RowState &st, int64_t w, int n_pos, int lane) {
+template <int MODE>
+__device__ __forceinline__ void flush_row(const MergeArgs &a, const RowStateT<MODE> &st, int64_t w, int n_pos, int lane) {
     if (st.rs == st.re) return;  // empty rows are zero-filled by the fix-up kernel
-    const uint2 hl = acc_hll(st);
+    const RowVec<MODE> r = acc_row<MODE>(st);
     if (st.rs >= 0 && st.re <= n_pos) {
-        store_row(a, st.cur, st.mh, hl, lane);
+        store_row<MODE>(a, st.cur, r, lane);
     } else {  // cut by a range boundary: partial record for the fix-up kernel
-        uint8_t *dst = a.scratch + (2 * w + (st.rs < 0 ? 0 : 1)) * (int64_t)REC;
-        st_na_u4(dst + lane * 16, st.mh);
-        st_na_u2(dst + REC_MH + lane * 8, hl);
+        stg_row<MODE>(a.scratch + (2 * w + (st.rs < 0 ? 0 : 1)) * (int64_t)Lay<MODE>::BYTES, r, lane);
     }
 }
 
 // move to the next row (the one starting at st.re)
-__device__ __forceinline__ void advance_row(const MergeArgs &a, RowState &st, int64_t s) {
+template <int MODE>
+__device__ __forceinline__ void advance_row(const MergeArgs &a, RowStateT<MODE> &st, int64_t s) {
     st.cur += 1;
     st.rs = st.re;
     st.re = st.re_next;
     st.re_next = ((int64_t)st.cur + 2 <= a.n_rows) ? rel_pos(__ldg(a.rowptr + st.cur + 2), s) : st.re;
-    acc_reset(st);
+    acc_reset<MODE>(st);
 }
 
-__device__ __forceinline__ void begin_range(const MergeArgs &a, RowState &st, int64_t s) {
+template <int MODE>
+__device__ __forceinline__ void begin_range(const MergeArgs &a, RowStateT<MODE> &st, int64_t s) {
     st.cur = (int)row_of_position(a.rowptr, a.n_rows, s);
     st.rs = rel_pos(__ldg(a.rowptr + st.cur), s);  // rowptr[cur] <= s: 0 if the row starts here, else -1
     st.re = rel_pos(__ldg(a.rowptr + st.cur + 1), s);
     st.re_next = ((int64_t)st.cur + 2 <= a.n_rows) ? rel_pos(__ldg(a.rowptr + st.cur + 2), s) : st.re;
-    acc_reset(st);
+    acc_reset<MODE>(st);
 }
+
+// kernels that belong to a memoised pipeline (the ELPH per-batch path) are launched with a GUARD: a device word that
+// says whether their cached result is still valid; they return at once when it is (no host synchronisation needed
+// to decide)
+__device__ __forceinline__ bool guarded_skip(const int *guard) { return guard && *reinterpret_cast<const volatile int *>(guard) == 0; }
 
 // ------------------------------------------------------------------------------------------------
 // LDG engine
 // ------------------------------------------------------------------------------------------------
 template <int U>
 __global__ void __launch_bounds__(256) merge_ldg_kernel(const MergeArgs a) {
+    constexpr int MODE = LAY_FULL;
+    if (guarded_skip(a.guard)) return;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -223,8 +311,8 @@ __global__ void __launch_bounds__(256) merge_ldg_kernel(const MergeArgs a) {
         const int64_t s = w * a.quantum;
         const int n_pos = (int)min((int64_t)a.quantum, a.nnz - s);
         if (n_pos <= 0) continue;  // nnz == 0
-        RowState st;
-        begin_range(a, st, s);
+        RowStateT<MODE> st;
+        begin_range<MODE>(a, st, s);
         const int32_t *__restrict__ ids_ptr = a.colidx + s;
         int32_t next_ids = (lane < n_pos) ? __ldg(ids_ptr + lane) : 0;
         for (int base = 0; base < n_pos; base += 32) {
@@ -232,31 +320,26 @@ __global__ void __launch_bounds__(256) merge_ldg_kernel(const MergeArgs a) {
             next_ids = (base + 32 + lane < n_pos) ? __ldg(ids_ptr + base + 32 + lane) : 0;
             const int cnt = min(32, n_pos - base);
             for (int j = 0; j < cnt; j += U) {
-                uint4 m[U];
-                uint2 h[U];
+                RowVec<MODE> rows[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int c = __shfl_sync(FULL, ids, (j + u) & 31);
-                    if (j + u < cnt) {
-                        const uint8_t *row = in + (int64_t)c * a.in_stride;
-                        m[u] = ld_nc_u4(row + lane * 16);
-                        h[u] = ld_nc_u2(row + REC_MH + lane * 8);
-                    }
+                    if (j + u < cnt) rows[u] = ldg_row<MODE>(in + (int64_t)c * a.in_stride, lane);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (j + u < cnt) {
                         const int pos = base + j + u;
                         while (pos == st.re) {
-                            flush_row(a, st, w, n_pos, lane);
-                            advance_row(a, st, s);
+                            flush_row<MODE>(a, st, w, n_pos, lane);
+                            advance_row<MODE>(a, st, s);
                         }
-                        acc_merge(st, m[u], h[u]);
+                        acc_merge<MODE>(st, rows[u]);
                     }
                 }
             }
         }
-        flush_row(a, st, w, n_pos, lane);
+        flush_row<MODE>(a, st, w, n_pos, lane);
     }
 }
 
@@ -315,12 +398,27 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     return r;
 }
 
-template <int S, int WARPS, int MIN_CTAS, bool GATHER4>
+__device__ __forceinline__ uint32_t lds_u1(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+template <int W>
+__device__ __forceinline__ void lds_words(uint32_t addr, uint32_t *w) {
+    if (W == 4) { const uint4 v = lds_u4(addr); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    if (W == 2) { const uint2 v = lds_u2(addr); w[0] = v.x; w[1] = v.y; }
+    if (W == 1) { w[0] = lds_u1(addr); }
+}
+
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const MergeArgs a,
                                                                            const __grid_constant__ CUtensorMap tmap) {
     constexpr int G = 4;
-    constexpr uint32_t STAGE = G * REC;
+    constexpr int RB = Lay<MODE>::BYTES;
+    constexpr int MW = Lay<MODE>::MW, HW = Lay<MODE>::HW;
+    constexpr uint32_t STAGE = G * RB;
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (guarded_skip(a.guard)) return;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (S * STAGE);
@@ -370,10 +468,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
                 if (GATHER4) {
                     tma_gather4(dst, &tmap, bar, 0, ids.x, ids.y, ids.z, ids.w);
                 } else {
-                    bulk_g2s32(dst, in + (uint64_t)(uint32_t)ids.x * in_stride, REC, bar);
-                    bulk_g2s32(dst + REC, in + (uint64_t)(uint32_t)ids.y * in_stride, REC, bar);
-                    bulk_g2s32(dst + 2 * REC, in + (uint64_t)(uint32_t)ids.z * in_stride, REC, bar);
-                    bulk_g2s32(dst + 3 * REC, in + (uint64_t)(uint32_t)ids.w * in_stride, REC, bar);
+                    bulk_g2s32(dst, in + (uint64_t)(uint32_t)ids.x * in_stride, RB, bar);
+                    bulk_g2s32(dst + RB, in + (uint64_t)(uint32_t)ids.y * in_stride, RB, bar);
+                    bulk_g2s32(dst + 2 * RB, in + (uint64_t)(uint32_t)ids.z * in_stride, RB, bar);
+                    bulk_g2s32(dst + 3 * RB, in + (uint64_t)(uint32_t)ids.w * in_stride, RB, bar);
                 }
             }
             issued += 1;
@@ -382,33 +480,35 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
 
         const int prologue = n_groups < S ? n_groups : S;
         for (int i = 0; i < prologue; ++i) issue();
-        RowState st;
-        begin_range(a, st, s);
+        RowStateT<MODE> st;
+        begin_range<MODE>(a, st, s);
 
         int pos = 0;
         for (int g = 0; g < n_groups; ++g) {
             mbar_wait32(bars + 8 * slot_c, par_c);
             const int cnt = min(G, n_pos - g * G);
-            const uint32_t rows = ring + slot_c * STAGE + lane * 16;
-            const uint32_t rows_h = ring + slot_c * STAGE + REC_MH + lane * 8;
+            const uint32_t rows = ring + slot_c * STAGE + lane * (4 * MW);
+            const uint32_t rows_h = ring + slot_c * STAGE + Lay<MODE>::MH_BYTES + lane * (4 * HW);
             int l = 0;
             while (l < cnt) {
                 while (pos == st.re) {
-                    flush_row(a, st, w, n_pos, lane);
-                    advance_row(a, st, s);
+                    flush_row<MODE>(a, st, w, n_pos, lane);
+                    advance_row<MODE>(a, st, s);
                 }
                 if (l + 1 < cnt && pos + 1 < st.re) {
-                    const uint4 m1 = lds_u4(rows + l * REC);
-                    const uint2 h1 = lds_u2(rows_h + l * REC);
-                    const uint4 m2 = lds_u4(rows + (l + 1) * REC);
-                    const uint2 h2 = lds_u2(rows_h + (l + 1) * REC);
-                    acc_merge2(st, m1, h1, m2, h2);
+                    RowVec<MODE> r1, r2;
+                    lds_words<MW>(rows + l * RB, r1.m);
+                    lds_words<HW>(rows_h + l * RB, r1.h);
+                    lds_words<MW>(rows + (l + 1) * RB, r2.m);
+                    lds_words<HW>(rows_h + (l + 1) * RB, r2.h);
+                    acc_merge2<MODE>(st, r1, r2);
                     l += 2;
                     pos += 2;
                 } else {
-                    const uint4 m1 = lds_u4(rows + l * REC);
-                    const uint2 h1 = lds_u2(rows_h + l * REC);
-                    acc_merge(st, m1, h1);
+                    RowVec<MODE> r1;
+                    lds_words<MW>(rows + l * RB, r1.m);
+                    lds_words<HW>(rows_h + l * RB, r1.h);
+                    acc_merge<MODE>(st, r1);
                     l += 1;
                     pos += 1;
                 }
@@ -421,14 +521,17 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
             __syncwarp();  // every lane has finished reading the slot before it is refilled
             if (issued < n_groups) issue();
         }
-        flush_row(a, st, w, n_pos, lane);
+        flush_row<MODE>(a, st, w, n_pos, lane);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // fix-up: fold the partial records of rows cut by range boundaries; zero-fill rows with no in-edge
 // ------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
+    constexpr int RB = Lay<MODE>::BYTES;
+    if (guarded_skip(a.guard)) return;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -441,32 +544,26 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
         const int64_t rs = __ldg(a.rowptr + last), re = __ldg(a.rowptr + last + 1);
         if (rs < s || re <= e) continue;  // started earlier (someone else folds) or not cut
         const int64_t w_end = (re - 1) / a.quantum;  // range holding the last neighbour
-        RowState st;
-        acc_reset(st);
-        {
-            const uint8_t *p = a.scratch + (2 * w + 1) * (int64_t)REC;
-            const uint4 m0 = ld_nc_u4(p + lane * 16);
-            const uint2 h0 = ld_nc_u2(p + REC_MH + lane * 8);
-            acc_merge(st, m0, h0);
-        }
+        RowStateT<MODE> st;
+        acc_reset<MODE>(st);
+        acc_merge<MODE>(st, ldg_row<MODE>(a.scratch + (2 * w + 1) * (int64_t)RB, lane));
         for (int64_t x = w + 1; x <= w_end; x += 4) {
-            uint4 m[4];
-            uint2 h[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (x + u <= w_end) {
-                    const uint8_t *p = a.scratch + (2 * (x + u)) * (int64_t)REC;
-                    m[u] = ld_nc_u4(p + lane * 16);
-                    h[u] = ld_nc_u2(p + REC_MH + lane * 8);
-                }
-            }
+            RowVec<MODE> r[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (x + u <= w_end) acc_merge(st, m[u], h[u]);
+                if (x + u <= w_end) r[u] = ldg_row<MODE>(a.scratch + (2 * (x + u)) * (int64_t)RB, lane);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (x + u <= w_end) acc_merge<MODE>(st, r[u]);
         }
-        store_row(a, last, st.mh, acc_hll(st), lane);
+        store_row<MODE>(a, last, acc_row<MODE>(st), lane);
     }
     // (B) rows without any in-edge: all-zero record (scatter-max fill value), cardinality of an empty sketch
+    RowVec<MODE> zero;
+#pragma unroll
+    for (int i = 0; i < (Lay<MODE>::MW > 0 ? Lay<MODE>::MW : 1); ++i) zero.m[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < (Lay<MODE>::HW > 0 ? Lay<MODE>::HW : 1); ++i) zero.h[i] = 0u;
     for (int64_t r0 = gwarp * 32; r0 < a.n_rows; r0 += n_warps * 32) {
         const int64_t r = r0 + lane;
         const bool empty = r < a.n_rows && __ldg(a.rowptr + r) == __ldg(a.rowptr + r + 1);
@@ -474,7 +571,7 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            store_row(a, r0 + b, make_uint4(0u, 0u, 0u, 0u), make_uint2(0u, 0u), lane);
+            store_row<MODE>(a, r0 + b, zero, lane);
         }
     }
 }
@@ -553,7 +650,8 @@ __global__ void __launch_bounds__(256) merge_generic_kernel(const GenericArgs a)
 template <typename T, bool IS_MIN>
 __global__ void __launch_bounds__(256) prop_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                                     int64_t n_rows, const T *__restrict__ x, T *__restrict__ out,
-                                                    int64_t width) {
+                                                    int64_t width, const int *guard = nullptr) {
+    if (guarded_skip(guard)) return;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -631,16 +729,16 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 2-D map over [n_rows x 192 uint32] with row pitch `stride` bytes; box = one row (gather4 fetches 4 boxes)
-static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_rows, int64_t stride) {
+// 2-D map over [n_rows x row_bytes / 4 uint32] with row pitch `stride` bytes; box = one row (gather4 fetches 4 boxes)
+static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_rows, int64_t stride, int row_bytes) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return SS_ERR_CUDA;
     }
-    cuuint64_t dims[2] = {(cuuint64_t)(REC / 4), (cuuint64_t)n_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)(row_bytes / 4), (cuuint64_t)n_rows};
     cuuint64_t strides[1] = {(cuuint64_t)stride};
-    cuuint32_t box[2] = {(cuuint32_t)(REC / 4), 1};
+    cuuint32_t box[2] = {(cuuint32_t)(row_bytes / 4), 1};
     cuuint32_t elem[2] = {1, 1};
     // L2 promotion = granularity of the L2 fills behind the gather (tuning knob SS_B200_TMA_L2PROMO = 0 / 64 / 128 / 256)
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
@@ -660,11 +758,11 @@ static int make_row_gather_map(CUtensorMap *map, const void *base, int64_t n_row
     return SS_OK;
 }
 
-// TMA engine configurations: (stages, warps per CTA, CTAs per SM).  Shared memory per warp = stages * 3 KB.
-template <int S, int WARPS, int MIN_CTAS, bool GATHER4>
+// TMA engine configurations: (stages, warps per CTA, CTAs per SM).  Shared memory per warp = stages * 4 rows.
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4, int MODE>
 static int launch_tma(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
-    constexpr size_t smem = (size_t)WARPS * S * 4 * REC + WARPS * S * 8;
-    auto k = merge_tma_kernel<S, WARPS, MIN_CTAS, GATHER4>;
+    constexpr size_t smem = (size_t)WARPS * S * 4 * Lay<MODE>::BYTES + WARPS * S * 8;
+    auto k = merge_tma_kernel<S, WARPS, MIN_CTAS, GATHER4, MODE>;
     SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = 0, rc;
     if ((rc = resident_grid(k, WARPS * 32, smem, &grid)) != SS_OK) return rc;
@@ -686,11 +784,41 @@ static int tma_config(int64_t nnz) {
 template <bool GATHER4>
 static int launch_tma_cfg(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
     switch (tma_config(a.nnz)) {
-        case 0: return launch_tma<4, 4, 4, GATHER4>(a, tmap, st);   // 16 warps / SM, 4 stages
-        case 2: return launch_tma<2, 4, 8, GATHER4>(a, tmap, st);   // 32 warps / SM, 2 stages
-        case 3: return launch_tma<6, 4, 3, GATHER4>(a, tmap, st);   // 12 warps / SM, 6 stages
-        case 4: return launch_tma<3, 8, 3, GATHER4>(a, tmap, st);   // 24 warps / SM, 3 stages, 8-warp CTAs
-        default: return launch_tma<3, 4, 6, GATHER4>(a, tmap, st);  // 24 warps / SM, 3 stages
+        case 0: return launch_tma<4, 4, 4, GATHER4, LAY_FULL>(a, tmap, st);   // 16 warps / SM, 4 stages
+        case 2: return launch_tma<2, 4, 8, GATHER4, LAY_FULL>(a, tmap, st);   // 32 warps / SM, 2 stages
+        case 3: return launch_tma<6, 4, 3, GATHER4, LAY_FULL>(a, tmap, st);   // 12 warps / SM, 6 stages
+        case 4: return launch_tma<3, 8, 3, GATHER4, LAY_FULL>(a, tmap, st);   // 24 warps / SM, 3 stages, 8-warp CTAs
+        default: return launch_tma<3, 4, 6, GATHER4, LAY_FULL>(a, tmap, st);  // 24 warps / SM, 3 stages
+    }
+}
+
+// narrower rows (one half of a record, or a column half): gather4 only; the ring is smaller, so more warps fit
+template <int MODE>
+static int launch_tma_narrow(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
+    switch (tma_config(a.nnz)) {
+        case 0: return launch_tma<4, 4, 6, true, MODE>(a, tmap, st);    // 24 warps / SM, 4 stages
+        case 2: return launch_tma<3, 4, 8, true, MODE>(a, tmap, st);    // 32 warps / SM, 3 stages
+        default: return launch_tma<4, 4, 8, true, MODE>(a, tmap, st);   // 32 warps / SM, 4 stages
+    }
+}
+
+template <int MODE>
+static int launch_fixup(const MergeArgs &a, cudaStream_t st) {
+    int64_t warps = a.n_ranges > (a.n_rows + 31) / 32 ? a.n_ranges : (a.n_rows + 31) / 32;
+    int64_t blocks = (warps + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 8;
+    merge_fixup_kernel<MODE><<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a);
+    SS_LAUNCH_CHECK("merge_fixup_kernel");
+    return SS_OK;
+}
+
+static int layout_bytes(int layout) {
+    switch (layout) {
+        case SS_LAYOUT_FULL: return Lay<LAY_FULL>::BYTES;
+        case SS_LAYOUT_MINHASH: return Lay<LAY_MH>::BYTES;
+        case SS_LAYOUT_HLL: return Lay<LAY_HLL>::BYTES;
+        case SS_LAYOUT_HALF: return Lay<LAY_HALF>::BYTES;
+        default: return -1;
     }
 }
 
@@ -722,40 +850,66 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
                         void *workspace, int64_t workspace_bytes, float *cards_out, int64_t cards_stride,
                         const ss_hll_consts *hc, int variant, int n_peers, void *const *peer_rec_out,
                         float *const *peer_cards_out, void *mc_rec_out, float *mc_cards_out, ss_stream_t stream) {
+    ss_merge_desc d;
+    memset(&d, 0, sizeof(d));
+    d.rowptr = rowptr; d.colidx = colidx; d.n_rows = n_rows; d.nnz = nnz;
+    d.rec_in = rec_in; d.in_rows = in_rows; d.in_stride = in_stride; d.rec_out = rec_out; d.out_stride = out_stride;
+    d.num_perm = num_perm; d.hll_p = hll_p; d.layout = SS_LAYOUT_FULL;
+    d.workspace = workspace; d.workspace_bytes = workspace_bytes;
+    d.cards_out = cards_out; d.cards_stride = cards_stride; d.hc = hc; d.variant = variant;
+    d.n_peers = n_peers; d.peer_rec_out = peer_rec_out; d.peer_cards_out = peer_cards_out;
+    d.mc_rec_out = mc_rec_out; d.mc_cards_out = mc_cards_out;
+    return ss_khop_merge_ex(&d, stream);
+}
+
+int ss_khop_merge_ex(const ss_merge_desc *d, ss_stream_t stream) {
+    SS_REQUIRE(d, "null descriptor passed to ss_khop_merge_ex");
+    const int num_perm = d->num_perm, hll_p = d->hll_p;
+    const int64_t n_rows = d->n_rows, nnz = d->nnz, in_rows = d->in_rows, in_stride = d->in_stride, out_stride = d->out_stride;
+    int variant = d->variant;
     ss::RecordShape s;
     SS_REQUIRE(ss::make_shape(num_perm, hll_p, &s), "unsupported sketch shape num_perm=%d hll_p=%d", num_perm, hll_p);
     SS_REQUIRE(n_rows >= 0 && nnz >= 0 && in_rows >= 0, "negative size passed to ss_khop_merge");
     SS_REQUIRE(in_rows < (1ll << 31), "at most 2^31-1 rows in the previous-hop table");
     if (n_rows == 0) return SS_OK;
     SS_REQUIRE(n_rows < (1ll << 31), "at most 2^31-1 rows per call");
-    SS_REQUIRE(rowptr && rec_in && rec_out, "null pointer passed to ss_khop_merge");
-    SS_REQUIRE(nnz == 0 || colidx, "colidx is null");
-    SS_REQUIRE((((uintptr_t)rec_in | (uintptr_t)rec_out) & 15) == 0, "record tables must be 16-byte aligned");
-    SS_REQUIRE(((uintptr_t)colidx & 15) == 0, "colidx must be 16-byte aligned");
-    SS_REQUIRE(in_stride >= s.bytes && out_stride >= s.bytes && ((in_stride | out_stride) & 15) == 0,
-               "record strides must be >= %d and multiples of 16", s.bytes);
+    SS_REQUIRE(d->rowptr && d->rec_in && d->rec_out, "null pointer passed to ss_khop_merge");
+    SS_REQUIRE(nnz == 0 || d->colidx, "colidx is null");
+    SS_REQUIRE((((uintptr_t)d->rec_in | (uintptr_t)d->rec_out) & 15) == 0, "record tables must be 16-byte aligned");
+    SS_REQUIRE(((uintptr_t)d->colidx & 15) == 0, "colidx must be 16-byte aligned");
+    const bool fast_shape = (num_perm == 128 && hll_p == 8);
+    const int row_bytes = d->layout == SS_LAYOUT_FULL ? s.bytes : ss::layout_bytes(d->layout);
+    SS_REQUIRE(row_bytes > 0, "unknown row layout %d", d->layout);
+    SS_REQUIRE(d->layout == SS_LAYOUT_FULL || fast_shape, "partial row layouts need num_perm=128, hll_p=8");
+    SS_REQUIRE(in_stride >= row_bytes && out_stride >= row_bytes && ((in_stride | out_stride) & 15) == 0,
+               "row strides must be >= %d and multiples of 16", row_bytes);
+    const bool want_cards = d->cards_out && (d->layout == SS_LAYOUT_FULL || d->layout == SS_LAYOUT_HLL);
+    SS_REQUIRE(!d->cards_out || want_cards, "cardinalities need all 256 registers of a row (FULL or HLL layout)");
     ss::HllDev hd;
     memset(&hd, 0, sizeof(hd));
-    if (cards_out) {
-        int rc = ss::check_hll_consts(hc, hll_p);
+    if (want_cards) {
+        int rc = ss::check_hll_consts(d->hc, hll_p);
         if (rc != SS_OK) return rc;
-        hd = ss::to_dev(hc);
+        hd = ss::to_dev(d->hc);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast_shape = (num_perm == 128 && hll_p == 8);
     if (variant == SS_MERGE_AUTO) variant = fast_shape ? SS_MERGE_TMA : SS_MERGE_GENERIC;
     SS_REQUIRE(variant == SS_MERGE_GENERIC || fast_shape, "TMA/LDG merge kernels need num_perm=128, hll_p=8");
+    SS_REQUIRE(d->layout == SS_LAYOUT_FULL || variant == SS_MERGE_TMA, "partial row layouts run on the TMA engine only");
 
+    const int n_peers = d->n_peers;
     SS_REQUIRE(n_peers >= 0 && n_peers <= SS_MAX_PEERS, "n_peers must be in [0, %d]", SS_MAX_PEERS);
-    SS_REQUIRE(n_peers == 0 || (variant != SS_MERGE_GENERIC && peer_rec_out && (!cards_out || peer_cards_out)),
+    SS_REQUIRE(n_peers == 0 || (variant != SS_MERGE_GENERIC && d->peer_rec_out && (!want_cards || d->peer_cards_out)),
                "peer stores need the P=128/p=8 engines and one pointer per peer");
-    SS_REQUIRE(!mc_rec_out || variant != SS_MERGE_GENERIC, "multicast stores need the P=128/p=8 engines");
+    SS_REQUIRE(!d->mc_rec_out || variant != SS_MERGE_GENERIC, "multicast stores need the P=128/p=8 engines");
+    SS_REQUIRE(!d->peer_mask || (n_peers > 0 && !d->mc_rec_out), "peer_mask selects among peer stores (not multicast)");
     if (variant == SS_MERGE_GENERIC) {
+        SS_REQUIRE(!d->guard, "guarded launches need the P=128/p=8 engines");
         ss::GenericArgs g;
-        g.rowptr = rowptr; g.colidx = colidx; g.n_rows = n_rows;
-        g.in = (const uint8_t *)rec_in; g.in_stride = in_stride;
-        g.out = (uint8_t *)rec_out; g.out_stride = out_stride;
-        g.cards = cards_out; g.cards_stride = cards_stride; g.s = s; g.h = hd;
+        g.rowptr = d->rowptr; g.colidx = d->colidx; g.n_rows = n_rows;
+        g.in = (const uint8_t *)d->rec_in; g.in_stride = in_stride;
+        g.out = (uint8_t *)d->rec_out; g.out_stride = out_stride;
+        g.cards = d->cards_out; g.cards_stride = d->cards_stride; g.s = s; g.h = hd;
         int64_t blocks = (n_rows + 7) / 8;
         int64_t cap = (int64_t)ss::sm_count() * 8;
         ss::merge_generic_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(g);
@@ -764,27 +918,30 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
     }
 
     ss::MergeArgs a;
-    a.rowptr = rowptr; a.colidx = colidx; a.n_rows = n_rows; a.nnz = nnz;
-    a.in = (const uint8_t *)rec_in; a.in_stride = in_stride;
-    a.out = (uint8_t *)rec_out; a.out_stride = out_stride;
+    memset(&a, 0, sizeof(a));
+    a.rowptr = d->rowptr; a.colidx = d->colidx; a.n_rows = n_rows; a.nnz = nnz;
+    a.in = (const uint8_t *)d->rec_in; a.in_stride = in_stride;
+    a.out = (uint8_t *)d->rec_out; a.out_stride = out_stride;
     a.quantum = ss::pick_quantum(nnz);
     a.n_ranges = ss::n_ranges_for(nnz, a.quantum);
-    a.scratch = (uint8_t *)workspace;
-    a.cards = cards_out; a.cards_stride = cards_stride; a.h = hd;
-    SS_REQUIRE(!mc_rec_out || (((uintptr_t)mc_rec_out & 15) == 0 && (!cards_out || mc_cards_out)),
+    a.scratch = (uint8_t *)d->workspace;
+    a.cards = want_cards ? d->cards_out : nullptr; a.cards_stride = d->cards_stride; a.h = hd;
+    SS_REQUIRE(!d->mc_rec_out || (((uintptr_t)d->mc_rec_out & 15) == 0 && (!want_cards || d->mc_cards_out)),
                "multicast table must be 16-byte aligned and come with a multicast cards pointer");
-    a.mc_out = (uint8_t *)mc_rec_out;
-    a.mc_cards = mc_rec_out ? mc_cards_out : nullptr;
+    a.mc_out = (uint8_t *)d->mc_rec_out;
+    a.mc_cards = d->mc_rec_out ? d->mc_cards_out : nullptr;
     a.n_peers = n_peers;
+    a.peer_mask = d->peer_mask;
+    a.guard = d->guard;
     for (int p = 0; p < SS_MAX_PEERS; ++p) {
-        a.peer_out[p] = p < n_peers ? (uint8_t *)peer_rec_out[p] : nullptr;
-        a.peer_cards[p] = (p < n_peers && cards_out) ? peer_cards_out[p] : nullptr;
+        a.peer_out[p] = p < n_peers ? (uint8_t *)d->peer_rec_out[p] : nullptr;
+        a.peer_cards[p] = (p < n_peers && want_cards) ? d->peer_cards_out[p] : nullptr;
         SS_REQUIRE(p >= n_peers || (a.peer_out[p] && ((uintptr_t)a.peer_out[p] & 15) == 0), "peer table %d is null or misaligned", p);
     }
-    const int64_t need = 2 * a.n_ranges * (int64_t)ss::REC;
-    SS_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "merge workspace must be a 16-byte aligned device buffer");
-    if (workspace_bytes < need) {
-        ss::set_error("merge workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+    const int64_t need = 2 * a.n_ranges * (int64_t)row_bytes;
+    SS_REQUIRE(d->workspace && ((uintptr_t)d->workspace & 15) == 0, "merge workspace must be a 16-byte aligned device buffer");
+    if (d->workspace_bytes < need) {
+        ss::set_error("merge workspace too small: %lld < %lld", (long long)d->workspace_bytes, (long long)need);
         return SS_ERR_WORKSPACE;
     }
     int grid = 0, rc;
@@ -794,8 +951,13 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
             memset(&tmap, 0, sizeof(tmap));
             if (variant == SS_MERGE_TMA) {
                 // rows addressed by colidx are < 2^31; the map covers every row the caller's table can hold
-                if ((rc = ss::make_row_gather_map(&tmap, rec_in, in_rows, in_stride)) != SS_OK) return rc;
-                rc = ss::launch_tma_cfg<true>(a, tmap, st);
+                if ((rc = ss::make_row_gather_map(&tmap, d->rec_in, in_rows, in_stride, row_bytes)) != SS_OK) return rc;
+                switch (d->layout) {
+                    case SS_LAYOUT_FULL: rc = ss::launch_tma_cfg<true>(a, tmap, st); break;
+                    case SS_LAYOUT_MINHASH: rc = ss::launch_tma_narrow<ss::LAY_MH>(a, tmap, st); break;
+                    case SS_LAYOUT_HLL: rc = ss::launch_tma_narrow<ss::LAY_HLL>(a, tmap, st); break;
+                    default: rc = ss::launch_tma_narrow<ss::LAY_HALF>(a, tmap, st); break;
+                }
             } else {
                 rc = ss::launch_tma_cfg<false>(a, tmap, st);
             }
@@ -812,14 +974,12 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
             return SS_ERR_INVALID;
         }
     }
-    {
-        int64_t warps = a.n_ranges > (n_rows + 31) / 32 ? a.n_ranges : (n_rows + 31) / 32;
-        int64_t blocks = (warps + 7) / 8;
-        int64_t cap = (int64_t)ss::sm_count() * 8;
-        ss::merge_fixup_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(a);
-        SS_LAUNCH_CHECK("merge_fixup_kernel");
+    switch (d->layout) {
+        case SS_LAYOUT_FULL: return ss::launch_fixup<ss::LAY_FULL>(a, st);
+        case SS_LAYOUT_MINHASH: return ss::launch_fixup<ss::LAY_MH>(a, st);
+        case SS_LAYOUT_HLL: return ss::launch_fixup<ss::LAY_HLL>(a, st);
+        default: return ss::launch_fixup<ss::LAY_HALF>(a, st);
     }
-    return SS_OK;
 }
 
 static int prop_grid(int64_t n_rows) {
@@ -830,10 +990,15 @@ static int prop_grid(int64_t n_rows) {
 
 int ss_prop_min_i64(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *x, int64_t *out,
                     int64_t width, ss_stream_t stream) {
+    return ss_prop_min_i64_guarded(rowptr, colidx, n_rows, x, out, width, nullptr, stream);
+}
+
+int ss_prop_min_i64_guarded(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *x, int64_t *out,
+                            int64_t width, const int32_t *guard, ss_stream_t stream) {
     SS_REQUIRE(n_rows >= 0 && width >= 0, "negative size passed to ss_prop_min_i64");
     if (n_rows == 0 || width == 0) return SS_OK;
     SS_REQUIRE(rowptr && x && out, "null pointer passed to ss_prop_min_i64");
-    ss::prop_kernel<int64_t, true><<<prop_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, n_rows, x, out, width);
+    ss::prop_kernel<int64_t, true><<<prop_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, n_rows, x, out, width, guard);
     SS_LAUNCH_CHECK("prop_kernel<int64,min>");
     return SS_OK;
 }

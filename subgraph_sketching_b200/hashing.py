@@ -154,35 +154,6 @@ def log2_window_table():
     return out
 
 
-class _CsrCache(object):
-    """destination-keyed CSR of the most recent edge_index, so that ELPH's per-batch hll_prop / minhash_prop
-    calls (models/elph.py:209-212: 2K calls per forward, same graph every batch) build it once.  The key is
-    the tensor's shape plus a content fingerprint computed on the device -- ELPH creates a fresh
-    `add_self_loops` tensor on every forward (often at a recycled address), so identity is not a safe key."""
-
-    def __init__(self):
-        self.key = None
-        self.value = None
-
-    @staticmethod
-    def fingerprint(ei):
-        if ei.shape[1] == 0:
-            return (0, 0)
-        a = ei[0] * 1000003 + ei[1]
-        n = ei.shape[1]
-        return (int(a.sum()), int((a[:: max(n // 64, 1)] * torch.arange(1, a[:: max(n // 64, 1)].numel() + 1,
-                                                                        device=ei.device)).sum()))
-
-    def get(self, edge_index, device, add_loops):
-        ei = edge_index.to(device, non_blocking=True) if edge_index.device != device else edge_index
-        ei = (ei if ei.dtype == torch.int64 else ei.long()).contiguous()
-        key = (tuple(ei.shape), str(device), add_loops, self.fingerprint(ei))
-        if key != self.key:
-            self.value = build_csr(ei, device, add_loops=add_loops)
-            self.key = key
-        return self.value
-
-
 def _edge_source(edge_index, device):
     """(tensor whose storage the CSR kernels read, zero_copy flag).  A pinned host edge_index is NOT copied:
     the kernels read it in place over PCIe with coalesced loads (UVA), so the list crosses the bus once and
@@ -373,12 +344,35 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
     return rowptr, colidx, nnz, max_id
 
 
+class _BareOwner(object):
+    """what a propagation operator constructed on its own (as the reference's module-level classes allow) needs of an
+    ElphHashes: no sketch shape, so only the plain kernels apply"""
+    num_perm, p, max_hops, event_log = 0, 0, 0, None
+
+    def __init__(self):
+        self._dev = {}
+
+    def _event_begin(self, device):
+        return None
+
+    def _event_end(self, name, start, device):
+        return None
+
+
+def _session_of(op):
+    from .session import PropagationSession
+    if op.owner is not None:
+        return op.owner._prop
+    if getattr(op, '_own_session', None) is None:
+        op._own_session = PropagationSession(_BareOwner())
+    return op._own_session
+
+
 class MinhashPropagation(object):
     """element-wise min over in-neighbours (hashing.py:28-35).  `edge_index` already holds the self loops."""
 
     def __init__(self, owner=None):
         self.owner = owner
-        self._csr = owner._csr_cache if owner is not None else _CsrCache()
 
     @torch.no_grad()
     def __call__(self, x, edge_index):
@@ -386,7 +380,7 @@ class MinhashPropagation(object):
 
     @torch.no_grad()
     def forward(self, x, edge_index):
-        return _propagate(x, edge_index, self._csr, True, self.owner)
+        return _propagate(x, edge_index, _session_of(self), True)
 
 
 class HllPropagation(object):
@@ -394,7 +388,6 @@ class HllPropagation(object):
 
     def __init__(self, owner=None):
         self.owner = owner
-        self._csr = owner._csr_cache if owner is not None else _CsrCache()
 
     @torch.no_grad()
     def __call__(self, x, edge_index):
@@ -402,40 +395,15 @@ class HllPropagation(object):
 
     @torch.no_grad()
     def forward(self, x, edge_index):
-        return _propagate(x, edge_index, self._csr, False, self.owner)
+        return _propagate(x, edge_index, _session_of(self), False)
 
 
-def _propagate(x, edge_index, cache, is_min, owner=None):
-    """operator form on the reference's tensors (ELPH calls it 2K times per forward, models/elph.py:209-212).
-    Sketch-shaped inputs (int64 [N,128] MinHash values in [0, 2^32) / int8 [N,256] registers >= 0) on graphs
-    that are worth it go through the record engine: pack -> hub-balanced TMA merge -> unpack.  Anything else
-    (other widths, other value ranges, tiny graphs) takes the plain row-per-warp kernel."""
-    device = _cuda_device(x)
-    want = torch.int64 if is_min else torch.int8
-    with torch.cuda.device(device):
-        xd = _to_device(x, device)
-        if xd.dtype != want:
-            xd = xd.to(want)
-        xd = xd.contiguous()
-        n, width = xd.shape
-        rowptr, colidx, nnz, max_id = cache.get(edge_index, device, False)
-        if max_id >= n:
-            raise IndexError(f'edge_index refers to node {max_id} but x has {n} rows')
-        if rowptr.numel() - 1 < n:  # nodes above max(edge_index): no in-edges -> zero rows
-            pad = rowptr[-1:].expand(n - (rowptr.numel() - 1))
-            rowptr = torch.cat([rowptr, pad])
-        out = None
-        if (owner is not None and owner.num_perm == 128 and owner.p == 8 and width == (128 if is_min else 256)
-                and nnz >= owner.fast_prop_min_nnz):
-            lo, hi = (int(v) for v in torch.aminmax(xd))
-            if lo >= 0 and hi < ((1 << 32) if is_min else 128):
-                out = owner._propagate_records(xd, rowptr, colidx, nnz, is_min, device)
-        if out is None:
-            out = torch.empty_like(xd)
-            fn = lib.ss_prop_min_i64 if is_min else lib.ss_prop_max_i8
-            check(fn(_ptr(rowptr), _ptr(colidx), n, _ptr(xd), _ptr(out), width, _stream_ptr(device)), 'ss_prop')
-        out = out.to(x.dtype) if out.dtype != x.dtype else out
-        return out if x.device == device else out.to(x.device)
+def _propagate(x, edge_index, session, is_min):
+    """operator form on the reference's tensors (ELPH calls it 2K times per forward, models/elph.py:209-212): see
+    session.PropagationSession -- cached CSR revalidated on the device, pair fusion, sketch reuse, half-record merges"""
+    if x.dim() != 2:
+        raise ValueError('x must be [n_nodes, width]')
+    return session.propagate(x, edge_index, is_min)
 
 
 class HopSketch(object):
@@ -521,8 +489,8 @@ class ElphHashes(object):
         self._minhash_range = (1 << 32)
         self.minhash_seed = 1
         self.num_perm = args.minhash_num_perm
-        self._csr_cache = _CsrCache()  # shared by both operators
-        self.fast_prop_min_nnz = 1 << 16  # operator forms use the record engine from this many neighbours up
+        from .session import PropagationSession
+        self._prop = PropagationSession(self)  # graph cache + memoised sketches shared by both operators
         self.minhash_prop = MinhashPropagation(self)
         # hll params (hashing.py:64-81)
         self.p = args.hll_p
@@ -692,28 +660,6 @@ class ElphHashes(object):
         end.record(torch.cuda.current_stream(device))
         self.event_log.append((name, start, end))
 
-    def _propagate_records(self, xd, rowptr, colidx, nnz, is_min, device):
-        """one operator-form hop through the record engine; the unused half of the records is never read back"""
-        n = xd.shape[0]
-        rb = self._record_bytes()
-        rec_in = torch.empty((n, rb), dtype=torch.uint8, device=device)
-        rec_out = torch.empty((n, rb), dtype=torch.uint8, device=device)
-        st = _stream_ptr(device)
-        if is_min:
-            rec_in[:, 4 * self.num_perm:].zero_()  # keep the (ignored) register half defined
-            check(lib.ss_pack_records(_ptr(xd), None, n, self.num_perm, self.p, _ptr(rec_in), rec_in.stride(0), st),
-                  'ss_pack_records')
-        else:
-            rec_in[:, :4 * self.num_perm].zero_()
-            check(lib.ss_pack_records(None, _ptr(xd), n, self.num_perm, self.p, _ptr(rec_in), rec_in.stride(0), st),
-                  'ss_pack_records')
-        self._merge(rowptr, colidx, nnz, rec_in, rec_out, None, device)
-        out = torch.empty_like(xd)
-        check(lib.ss_unpack_records(_ptr(rec_out), rec_out.stride(0), n, self.num_perm, self.p,
-                                    _ptr(out) if is_min else None, None if is_min else _ptr(out), st),
-              'ss_unpack_records')
-        return out
-
     def _alloc_hop_tables(self, num_nodes, rb, device):
         """K+1 record tables [num_nodes, rb] (uint8), row pitch = record_stride when that is set and affordable"""
         stride = rb
@@ -819,8 +765,11 @@ class ElphHashes(object):
         rb = self._record_bytes()
         for k in range(1, self.max_hops + 1):
             entry = dict.__getitem__(hash_table, k) if isinstance(hash_table, SketchTables) else hash_table[k]
+            memo = None if isinstance(entry, HopSketch) else self._prop.records_of(entry)
             if isinstance(entry, HopSketch) and entry.records.device == device:
                 rec = entry.records
+            elif memo is not None and memo.device == device:
+                rec = memo  # the dict ELPH.forward assembled from this engine's own operator outputs
             else:
                 mh = _to_device(entry['minhash'], device)
                 hl = _to_device(entry['hll'], device)
@@ -1028,6 +977,9 @@ class ElphHashes(object):
         @param regs: A tensor of registers [n_nodes, register_size] (or one row)
         @return: float32 [n_nodes] on regs.device
         """
+        memo = self._prop.cards_of(regs) if regs.dim() == 2 else None
+        if memo is not None:  # registers this engine merged itself: the merge epilogue already counted them
+            return memo
         if regs.dim() == 1:
             regs = regs.unsqueeze(dim=0)
         if regs.shape[1] != self.m:

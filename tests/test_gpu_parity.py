@@ -336,7 +336,7 @@ def test_elph_forward_call_pattern():
     ei_d = ei.to(DEV)
     init_hashes = eh.initialise_minhash(n).to(DEV)
     init_hll = eh.initialise_hll(n).to(DEV)
-    for forward_call in range(2):  # second call hits the CSR cache although the loop tensor is a new object
+    for forward_call in range(3):  # later calls hit the graph cache although the loop tensor is a new object
         hash_edge_index = so.with_self_loops(ei_d)
         cards = torch.zeros((n, K))
         table = {}
@@ -510,8 +510,10 @@ def test_pinned_host_inputs_are_read_in_place(monkeypatch):
 
 
 def test_operator_forms_use_record_engine_on_large_graphs():
-    """hll_prop / minhash_prop on a hub-heavy graph: the record-engine route (pack -> TMA merge -> unpack) and the
-    plain row-per-warp kernels must agree with the oracle and with each other; out-of-range values fall back"""
+    """hll_prop / minhash_prop called singly on a hub-heavy graph: the half-record TMA merges (registers in place of
+    the int8 tensor, MinHash through a 512-byte packed table) and the plain row-per-warp kernels (what an operator
+    constructed on its own uses) agree with the oracle and with each other; values outside the sketch range keep the
+    reference's exact signed semantics"""
     scale = 13
     n = 1 << scale
     ei = so.with_self_loops(rmat_edges(scale, 16, 11))
@@ -519,18 +521,104 @@ def test_operator_forms_use_record_engine_on_large_graphs():
     mh0, hl0 = eh.initialise_minhash(n), eh.initialise_hll(n)
     want_m, want_h = so.minhash_propagate(mh0, ei), so.hll_propagate(hl0, ei)
     ei_d, mh_d, hl_d = ei.to(DEV), mh0.to(DEV), hl0.to(DEV)
-    assert ei.shape[1] >= eh.fast_prop_min_nnz
-    fast_m, fast_h = eh.minhash_prop(mh_d, ei_d), eh.hll_prop(hl_d, ei_d)
-    eh.fast_prop_min_nnz = 1 << 62
-    slow_m, slow_h = eh.minhash_prop(mh_d, ei_d), eh.hll_prop(hl_d, ei_d)
-    eh.fast_prop_min_nnz = 1 << 16
+    fast_m = eh.minhash_prop(mh_d, ei_d)
+    assert eh._prop.stats['single_merges'] == 1 and eh._prop.stats['plain_calls'] == 0
+    eh2 = ssb.ElphHashes(make_args(2))
+    fast_h = eh2.hll_prop(hl_d, ei_d)
+    assert eh2._prop.stats['single_merges'] == 1
+    slow_m, slow_h = ssb.MinhashPropagation()(mh_d, ei_d), ssb.HllPropagation()(hl_d, ei_d)
     assert torch.equal(fast_m.cpu(), want_m) and torch.equal(slow_m, fast_m)
     assert torch.equal(fast_h.cpu(), want_h) and torch.equal(slow_h, fast_h)
-    # values outside the sketch range (negative / >= 2^32) keep the exact int64 semantics of the reference
+    # values outside the sketch range (negative / >= 2^32) keep the exact int64 semantics of the reference: the
+    # guarded plain kernel takes over on the device, no host round trip decides it
     weird = mh_d.clone()
     weird[5, 7] = -3
     weird[9, 1] = 1 << 40
-    assert torch.equal(eh.minhash_prop(weird, ei_d).cpu(), so.minhash_propagate(weird.cpu(), ei))
+    assert torch.equal(ssb.ElphHashes(make_args(2)).minhash_prop(weird, ei_d).cpu(), so.minhash_propagate(weird.cpu(), ei))
+    # registers are merged as SIGNED bytes, like the reference's int8 scatter-max
+    signed = hl_d.clone()
+    signed[torch.rand(signed.shape, device=DEV) < 0.01] = -7
+    signed[3, :] = -128
+    assert torch.equal(ssb.ElphHashes(make_args(2)).hll_prop(signed, ei_d).cpu(), so.hll_propagate(signed.cpu(), ei))
+    # other widths / dtypes take the plain kernels
+    narrow = torch.randint(-50, 50, (n, 40), device=DEV)
+    assert torch.equal(eh.minhash_prop(narrow, ei_d).cpu(), so.minhash_propagate(narrow.cpu(), ei))
+
+
+def test_elph_session_fusion_reuse_and_graph_changes():
+    """the memoised per-batch path (session.py) under the reference's training-loop pattern: a fresh add_self_loops
+    tensor every forward, the previous forward's dict still alive while the next one runs.  Every forward is bit-equal
+    to the oracle; from the second forward on the two operators of a hop share ONE fused merge; from the third on the
+    generations are re-enqueued guarded (graph unchanged -> kernels return at once); a different graph of the same
+    shape is noticed on the device and recomputed, without touching tensors the caller still holds"""
+    n, K = 4000, 2
+    g = torch.Generator().manual_seed(5)
+    graphs = [torch.randint(0, n - 50, (2, 30000), generator=g) for _ in range(2)]
+    oracles = []
+    o = so.OracleSketches(K, 128, 8, use_zero_one=False, floor_sf=False)
+    for ei in graphs:
+        oracles.append(o.build_hash_tables(n, ei))
+    links = torch.randint(0, n, (3000, 2), generator=g)
+    eh = ssb.ElphHashes(make_args(K))
+    init_hashes = eh.initialise_minhash(n).to(DEV)
+    init_hll = eh.initialise_hll(n).to(DEV)
+    def forward(gi):
+        hash_edge_index = so.with_self_loops(graphs[gi].to(DEV))       # a new tensor object every forward
+        cards = torch.zeros((n, K))
+        table = {0: {'minhash': init_hashes, 'hll': init_hll}}
+        for k in range(1, K + 1):
+            table[k] = {'hll': eh.hll_prop(table[k - 1]['hll'], hash_edge_index),
+                        'minhash': eh.minhash_prop(table[k - 1]['minhash'], hash_edge_index)}
+            cards[:, k - 1] = eh.hll_count(table[k]['hll'])
+        feats = eh.get_subgraph_features(links.to(DEV), table, cards)
+        return table, cards, feats
+
+    def check(out, gi):
+        table, cards, feats = out
+        ot, oc = oracles[gi]
+        for k in range(K + 1):
+            assert torch.equal(table[k]['minhash'].cpu(), ot[k]['minhash']), (gi, k)
+            assert torch.equal(table[k]['hll'].cpu(), ot[k]['hll']), (gi, k)
+        ok, err = float_close(cards, oc, oc)
+        assert ok, err
+        ok, err = float_close(feats.cpu(), o.subgraph_features(links, ot, oc), link_scale(links, oc))
+        assert ok, err
+
+    sequence = [0, 0, 0, 0, 0, 1, 1, 1, 0, 0]
+    prev = None
+    for step, gi in enumerate(sequence):
+        before = dict(eh._prop.stats)
+        cur = forward(gi)
+        check(cur, gi)
+        if prev is not None:
+            check(prev[0], prev[1])           # what the caller still holds was not overwritten
+        st = eh._prop.stats
+        if step == 0:
+            assert st['single_merges'] == 2 * K and st['fused_merges'] == 0
+        else:
+            assert st['single_merges'] == before['single_merges'], 'every later forward is fused'
+            assert st['fused_merges'] == before['fused_merges'] + K
+        # two generations alternate (the caller holds the previous forward's): the one of forward step-2 can be
+        # re-enqueued guarded iff the graph did not change between step-2 and step-1
+        if step >= 3 and sequence[step - 1] == sequence[step - 2]:
+            assert st['guarded'] == before['guarded'] + 1, 'generations are re-enqueued guarded'
+        prev = (cur, gi)
+    # CPU tensors take the same path (transparent offload), results on the CPU
+    eh_c = ssb.ElphHashes(make_args(K))
+    mh0, hl0 = eh_c.initialise_minhash(n), eh_c.initialise_hll(n)
+    for _ in range(2):
+        e = so.with_self_loops(graphs[1])
+        h1, m1 = eh_c.hll_prop(hl0, e), eh_c.minhash_prop(mh0, e)
+        h2, m2 = eh_c.hll_prop(h1, e), eh_c.minhash_prop(m1, e)
+        assert not h2.is_cuda and torch.equal(h2, oracles[1][0][2]['hll']) and torch.equal(m2, oracles[1][0][2]['minhash'])
+        assert torch.equal(h1, oracles[1][0][1]['hll']) and torch.equal(m1, oracles[1][0][1]['minhash'])
+    # node ids are validated on the device and reported at a later call
+    bad = so.with_self_loops(graphs[0]).to(DEV)
+    bad[0, 17] = n + 3
+    eh.hll_prop(init_hll, bad)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        eh.hll_prop(init_hll, so.with_self_loops(graphs[0].to(DEV)))
 
 
 def test_link_features_exact_path_for_large_registers():
