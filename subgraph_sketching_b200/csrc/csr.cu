@@ -368,6 +368,7 @@ __device__ __forceinline__ uint32_t fp_mix_b(uint32_t x, uint32_t y, uint32_t ke
 }
 
 __global__ void __launch_bounds__(256) sorted_csr_kernel(const SortedArgs a) {
+    constexpr int UNR = 4;  // 32-edge windows per trip: their loads are issued together (memory-level parallelism)
     const int lane = threadIdx.x & 31;
     unsigned long long fa = 0, fb = 0, ra = 0, rb = 0;
     int mx = -1, mn = 0x7fffffff;
@@ -375,76 +376,93 @@ __global__ void __launch_bounds__(256) sorted_csr_kernel(const SortedArgs a) {
     bool dead = false;  // an order violation was seen (by this warp or any other): the result will be discarded
     unsigned long long *st = (unsigned long long *)a.stats;
     const uint32_t ka = (uint32_t)a.ka, kb = (uint32_t)a.kb;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // whole warps iterate together (the tail is padded with inactive lanes) so that shuffles are well defined
-    const int64_t n_pad = (a.n + 31) & ~(int64_t)31;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        const bool live = i < a.n;
-        const int64_t k64 = live ? a.key[i] : 0;
-        const int64_t v64 = live ? a.val[i] : 0;
-        // ids outside [0, 2^31) are range errors; inside the loop everything is 32-bit (-2 marks an invalid id)
-        const bool id_ok = ((uint64_t)k64 | (uint64_t)v64) < (1ull << 31);
-        const int k = id_ok ? (int)k64 : -2, v = id_ok ? (int)v64 : -2;
-        int kp = __shfl_up_sync(FULL, k, 1);
-        int vp = __shfl_up_sync(FULL, v, 1);
-        if (lane == 0) {
-            if (i > 0) {
-                const int64_t a0 = a.key[i - 1], a1 = a.val[i - 1];
-                const bool okp = ((uint64_t)a0 | (uint64_t)a1) < (1ull << 31);
-                kp = okp ? (int)a0 : -2; vp = okp ? (int)a1 : -2;
-            } else if (a.e_base > a.e_origin) {
-                const int64_t a0 = a.carry[0], a1 = a.carry[1];
-                const bool okp = ((uint64_t)a0 | (uint64_t)a1) < (1ull << 31);
-                kp = okp ? (int)a0 : -2; vp = okp ? (int)a1 : -2;
-            } else { kp = (int)a.row_begin - 1; vp = -1; }
+    const int row_lo = (int)a.row_begin, row_hi = (int)(a.row_begin + a.n_rows);
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // a warp owns UNR consecutive windows per trip: [w0, w0 + 32 UNR); whole warps iterate together so that the
+    // shuffles are well defined (the tail is padded with inactive lanes)
+    for (int64_t w0 = gwarp * (32 * UNR); w0 < a.n; w0 += n_warps * (32 * UNR)) {
+        int64_t k64[UNR], v64[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = w0 + u * 32 + lane;
+            k64[u] = i < a.n ? a.key[i] : 0;
+            v64[u] = i < a.n ? a.val[i] : 0;
         }
-        const int64_t e = a.e_base + i - a.e_origin;   // position among the edges of this CSR
-        const int row_lo = (int)a.row_begin, row_hi = (int)(a.row_begin + a.n_rows);
-        bool ok = live && id_ok && k >= row_lo && k < row_hi && kp >= row_lo - 1;
-        if (live) {
-            if (!id_ok || k < row_lo || k >= row_hi) bad_range = 1;
-            if (id_ok) { mx = max(mx, max(k, v)); mn = min(mn, min(k, v)); }
-            else { mn = min(mn, (k64 < 0 || v64 < 0) ? -1 : mn); mx = max(mx, (k64 >= (1ll << 31) || v64 >= (1ll << 31)) ? 0x7fffffff : mx); }
-            if (v < vp) bad_val = 1;   // (only meaningful for the caller's "is the OTHER row ordered" question)
+        // the edge in front of this trip (lane 0 of the first window needs it)
+        int64_t p0 = -1, p1 = -1;
+        bool have_prev = false;
+        if (lane == 0) {
+            if (w0 > 0) { p0 = a.key[w0 - 1]; p1 = a.val[w0 - 1]; have_prev = true; }
+            else if (a.e_base > a.e_origin) { p0 = a.carry[0]; p1 = a.carry[1]; have_prev = true; }
         }
         // The pass is speculative.  On an unordered list the "rows that start here" ranges below are garbage and
         // could add up to E * n_rows writes, so all structural work stops as soon as ANY warp has seen a violation
-        // (each 32-edge window is checked before it is acted upon; the global counter is polled once per window).
-        const bool viol = __any_sync(FULL, live && k < kp);
-        if (viol && !dead && lane == 0) atomicAdd(st + 8, 1ull);
-        dead = dead || viol;
+        // (every window is checked before it is acted upon; the global counter is polled once per trip).
         if (!dead) dead = __any_sync(FULL, *(volatile unsigned long long *)(st + 8) != 0ull);
-        if (live && i == a.n - 1) { a.carry[0] = k64; a.carry[1] = v64; }  // read by the next chunk (stream order)
-        if (dead) continue;
-        if (live) {
-            const uint32_t hf = fp_mix_a((uint32_t)k, (uint32_t)v, ka), hr = fp_mix_a((uint32_t)v, (uint32_t)k, ka);
-            fa += hf; ra += hr;
-            fb += fp_mix_b((uint32_t)k, (uint32_t)v, kb); rb += fp_mix_b((uint32_t)v, (uint32_t)k, kb);
-        }
-        // rows (kp, k] start at this edge.  Short gaps inline; long ones (runs of rows without edges) warp-wide
-        const int gap = (ok && k > kp) ? (k - kp) : 0;
-        if (gap > 0 && gap <= 4) {
-            for (int r = kp + 1; r <= k; ++r) {
-                const int64_t pos = e + (a.loops ? r - row_lo : 0);
-                a.rowptr[r - row_lo] = pos;
-                if (a.loops && pos < a.capacity) a.colidx[pos] = r;
+        int kp_carry = 0, vp_carry = 0;  // last edge of the previous window (lane 31's values)
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = w0 + u * 32 + lane;
+            if (w0 + u * 32 >= a.n) break;  // warp-uniform
+            const bool live = i < a.n;
+            // ids outside [0, 2^31) are range errors; inside the loop everything is 32-bit (-2 marks an invalid id)
+            const bool id_ok = ((uint64_t)k64[u] | (uint64_t)v64[u]) < (1ull << 31);
+            const int k = id_ok ? (int)k64[u] : -2, v = id_ok ? (int)v64[u] : -2;
+            int kp = __shfl_up_sync(FULL, k, 1);
+            int vp = __shfl_up_sync(FULL, v, 1);
+            if (lane == 0) {
+                if (u > 0) { kp = kp_carry; vp = vp_carry; }
+                else if (have_prev) {
+                    const bool okp = ((uint64_t)p0 | (uint64_t)p1) < (1ull << 31);
+                    kp = okp ? (int)p0 : -2; vp = okp ? (int)p1 : -2;
+                } else { kp = row_lo - 1; vp = -1; }
             }
-        }
-        unsigned longs = __ballot_sync(FULL, gap > 4);
-        while (longs) {
-            const int b = __ffs(longs) - 1;
-            longs &= longs - 1;
-            const int r0 = __shfl_sync(FULL, kp, b) + 1, r1 = __shfl_sync(FULL, k, b);
-            const int64_t eb = a.e_base + (i - lane + b) - a.e_origin;
-            for (int r = r0 + lane; r <= r1; r += 32) {
-                const int64_t pos = eb + (a.loops ? r - row_lo : 0);
-                a.rowptr[r - row_lo] = pos;
-                if (a.loops && pos < a.capacity) a.colidx[pos] = r;
+            kp_carry = __shfl_sync(FULL, k, 31);
+            vp_carry = __shfl_sync(FULL, v, 31);
+            const int64_t e = a.e_base + i - a.e_origin;   // position among the edges of this CSR
+            const bool ok = live && id_ok && k >= row_lo && k < row_hi && kp >= row_lo - 1;
+            if (live) {
+                if (!id_ok || k < row_lo || k >= row_hi) bad_range = 1;
+                if (id_ok) { mx = max(mx, max(k, v)); mn = min(mn, min(k, v)); }
+                else { mn = (k64[u] < 0 || v64[u] < 0) ? -1 : mn; mx = (k64[u] >= (1ll << 31) || v64[u] >= (1ll << 31)) ? 0x7fffffff : mx; }
+                if (v < vp) bad_val = 1;   // (only meaningful for the caller's "is the OTHER row ordered" question)
+                if (i == a.n - 1) { a.carry[0] = k64[u]; a.carry[1] = v64[u]; }  // read by the next chunk (stream order)
             }
-        }
-        if (ok) {
-            const int64_t pos = e + (a.loops ? k - row_lo + 1 : 0);
-            if (pos < a.capacity) a.colidx[pos] = v;
+            const bool viol = __any_sync(FULL, live && k < kp);
+            if (viol && !dead && lane == 0) atomicAdd(st + 8, 1ull);
+            dead = dead || viol;
+            if (dead) continue;
+            if (live) {
+                const uint32_t hf = fp_mix_a((uint32_t)k, (uint32_t)v, ka), hr = fp_mix_a((uint32_t)v, (uint32_t)k, ka);
+                fa += hf; ra += hr;
+                fb += fp_mix_b((uint32_t)k, (uint32_t)v, kb); rb += fp_mix_b((uint32_t)v, (uint32_t)k, kb);
+            }
+            // rows (kp, k] start at this edge.  Short gaps inline; long ones (runs of rows without edges) warp-wide
+            const int gap = (ok && k > kp) ? (k - kp) : 0;
+            if (gap > 0 && gap <= 4) {
+                for (int r = kp + 1; r <= k; ++r) {
+                    const int64_t pos = e + (a.loops ? r - row_lo : 0);
+                    a.rowptr[r - row_lo] = pos;
+                    if (a.loops && pos < a.capacity) a.colidx[pos] = r;
+                }
+            }
+            unsigned longs = __ballot_sync(FULL, gap > 4);
+            while (longs) {
+                const int b = __ffs(longs) - 1;
+                longs &= longs - 1;
+                const int r0 = __shfl_sync(FULL, kp, b) + 1, r1 = __shfl_sync(FULL, k, b);
+                const int64_t eb = a.e_base + (w0 + u * 32 + b) - a.e_origin;
+                for (int r = r0 + lane; r <= r1; r += 32) {
+                    const int64_t pos = eb + (a.loops ? r - row_lo : 0);
+                    a.rowptr[r - row_lo] = pos;
+                    if (a.loops && pos < a.capacity) a.colidx[pos] = r;
+                }
+            }
+            if (ok) {
+                const int64_t pos = e + (a.loops ? k - row_lo + 1 : 0);
+                if (pos < a.capacity) a.colidx[pos] = v;
+            }
         }
     }
 #pragma unroll

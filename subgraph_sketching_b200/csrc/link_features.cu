@@ -332,6 +332,11 @@ __device__ __forceinline__ void lk_cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void lk_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void lk_cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void lk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void lk_cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void lk_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // which rank owns row `node` (row blocks are contiguous: bounds[q] <= node < bounds[q + 1])
@@ -355,6 +360,7 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
     constexpr int F = K * (K + 2);
     constexpr int EQW = (C + 3) / 4, NZW = (C + 2) / 3;
     __shared__ float stage_all[8][B * F];
+    __shared__ float cards_all[8][B * 2 * K];  // cards of the batch's endpoints, fetched asynchronously at batch start
     // endpoints of the current and the next tile of every warp (cp.async: no register staging, the load of the
     // next tile -- a PCIe round trip when the link list is a pinned host buffer -- overlaps the current tile)
     __shared__ __align__(16) longlong2 ids_all[8][2][LK_TILE_MAX];
@@ -373,6 +379,7 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
         const int cnt = (int)min((int64_t)tile, a.n_links - base);
         for (int x = lane; x < cnt; x += 32)
             lk_cp_async16(smem_u32(&ids_all[warp][buf][x]), reinterpret_cast<const longlong2 *>(a.links) + base + x);
+        lk_cp_async_commit();
     };
     int buf = 0;
     if (gwarp < n_tiles) fetch_ids(gwarp, 0);
@@ -395,6 +402,17 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
         int u_cur = -1;
         for (int b0 = 0; b0 < cnt; b0 += B) {
             const int nb = min(B, cnt - b0);
+            // the cardinalities the algebra of this batch will need: in flight (no registers) during the K^2 merges,
+            // instead of a dependent DRAM round trip in front of every batch's algebra
+            if (a.features && lane < nb) {
+                const int2 ec = reinterpret_cast<const int2 *>(ids + b0 + lane)[0];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    lk_cp_async4(smem_u32(&cards_all[warp][lane * 2 * K + k]), a.cards + (int64_t)ec.x * a.cards_stride + k);
+                    lk_cp_async4(smem_u32(&cards_all[warp][lane * 2 * K + K + k]), a.cards + (int64_t)ec.y * a.cards_stride + k);
+                }
+            }
+            lk_cp_async_commit();
             uint32_t my_lo = 0, my_hi = 0, my_match = 0;
             int my_zeros = 0;
             float my_Sx = -1.f;  // >= 0: exact-path sum (some register > 28)
@@ -420,6 +438,8 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
                     }
                 }
                 const bool sharded = a.n_ranks > 1;
+                const int ow_v = sharded ? lk_owner(a, v) : 0;
+                const bool have_v = sharded ? (__ldg(a.local_rows + v) != 0) : true;
                 if (u != u_cur) {  // warp-uniform: a run of links with the same source keeps u's prepared records
                     u_cur = u;
                     big_u = 0;
@@ -435,8 +455,6 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
                 }
                 RowRegsB V[K];
                 uint32_t big = big_u;
-                const int ow_v = sharded ? lk_owner(a, v) : 0;
-                const bool have_v = sharded ? (__ldg(a.local_rows + v) != 0) : true;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const uint8_t *rv = lk_table(a, k + 1, K, ow_v, have_v) + (int64_t)v * a.stride[k + 1];
@@ -524,13 +542,14 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
                 float I[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, jj * C + c);
-                const int2 e = reinterpret_cast<const int2 *>(ids + b0 + jj)[0];
-                const int64_t u = e.x, v = e.y;
+                // everything but the next tile's ids (the youngest group, if one is in flight) has landed
+                lk_cp_async_wait();
+                __syncwarp();
                 float cu[K], cv[K], f[F];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    cu[k] = __ldg(a.cards + u * a.cards_stride + k);
-                    cv[k] = __ldg(a.cards + v * a.cards_stride + k);
+                    cu[k] = cards_all[warp][jj * 2 * K + k];
+                    cv[k] = cards_all[warp][jj * 2 * K + K + k];
                 }
                 feature_algebra<K>(I, cu, cv, f);
                 knockout_and_floor<K>(f, a.flags);
@@ -809,7 +828,7 @@ static int launch_links(const LinkArgs &a, const int64_t *hop_rows, bool fast, c
         const int64_t n_tiles = (a.n_links + tile - 1) / tile;
         int64_t bl = (n_tiles + 7) / 8;
         int64_t cap_b = (int64_t)sm_count() * 3;
-        int prefetch = 1;
+        int prefetch = 0;  // measured: prefetch.global.L2 of the next link's 36 lines costs more than it hides (27.2 vs 23.5 ms)
         if (const char *e = getenv("SS_B200_LINK_PREFETCH")) prefetch = atoi(e);  // tuning knob
         link_features_batched_kernel<K><<<(int)(bl < cap_b ? bl : cap_b), 256, 0, st>>>(a, (int)tile, prefetch);
         SS_LAUNCH_CHECK("link_features_batched_kernel");

@@ -409,12 +409,20 @@ def _propagate(x, edge_index, session, is_min):
 class HopSketch(object):
     """one hop of a SketchTables: behaves like {'hll': int8 [N, m], 'minhash': int64 [N, P]}"""
 
-    def __init__(self, records, num_perm, p, out_device):
-        self.records = records  # uint8 [N, record_bytes] on the GPU
+    def __init__(self, records, num_perm, p, out_device, lease=None):
+        self._records = records  # uint8 [N, record_bytes] on the GPU
+        self._lease = lease      # [True] while the buffer still belongs to this table (see dist.ShardedElphHashes)
         self.num_perm = num_perm
         self.p = p
         self.out_device = out_device
         self._cache = {}
+
+    @property
+    def records(self):
+        if self._lease is not None and not self._lease[0]:
+            raise RuntimeError('these sketch tables live in buffers that a later build_hash_tables of the same sharded '
+                               'engine has reused; build with reuse_buffers=False to keep several alive')
+        return self._records
 
     def keys(self):
         return ['hll', 'minhash']
@@ -829,7 +837,7 @@ class ElphHashes(object):
             inter = inter if edge_list.device == device else _to_host(inter)
             return {(k1, k2): inter[:, (k1 - 1) * K + (k2 - 1)] for k1 in range(1, K + 1) for k2 in range(1, K + 1)}
 
-    def get_subgraph_features(self, links, hash_table, cards, batch_size=11000000):
+    def get_subgraph_features(self, links, hash_table, cards, batch_size=11000000, _shard=None):
         """
         structural features of each link: hop-wise intersection / difference cardinalities
         (hashing.py:258-323)
@@ -867,9 +875,10 @@ class ElphHashes(object):
 
             def launch(link_rows, out_rows):
                 ev = self._event_begin(device)
-                check(lib.ss_link_features(_ptr(link_rows), link_rows.shape[0], views, K, self.num_perm, self.p, _ptr(cd),
-                                           cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out_rows), None, _ptr(err),
-                                           _stream_ptr(device)), 'ss_link_features')
+                check(lib.ss_link_features_sharded(_ptr(link_rows), link_rows.shape[0], views, K, self.num_perm, self.p,
+                                                   _ptr(cd), cd.stride(0), ctypes.byref(d['hc']), flags, _ptr(out_rows),
+                                                   None, _ptr(err), ctypes.byref(_shard) if _shard is not None else None,
+                                                   _stream_ptr(device)), 'ss_link_features')
                 self._event_end('link_features', ev, device)
 
             if links.device == device:

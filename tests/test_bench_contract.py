@@ -20,6 +20,7 @@ def test_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': 'links/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'].startswith('rmat24') and d['vs_baseline'] is None
+    assert d['native_so_loaded'] == [], 'the reference arm must not map any library of this repository'
 
 
 def test_reference_arm_non_zero_ranks_stay_silent():

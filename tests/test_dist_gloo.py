@@ -76,3 +76,25 @@ def _worker(rank, world, port, n, width):
 
 def test_exchange_layout_world2():
     mp.spawn(_worker, args=(2, _free_port(), 37, 48), nprocs=2, join=True)
+
+
+def test_halo_masks_and_cumulative_shares():
+    """host logic of the halo push: who reads which of my rows, which rows my own copy holds"""
+    from subgraph_sketching_b200.dist import cumulative_shares, halo_masks
+    assert cumulative_shares(1) == []
+    assert cumulative_shares(4) == [0.25, 0.5, 0.75]
+    c = cumulative_shares(3, [2.0, 1.0, 1.0])
+    assert abs(c[0] - 0.5) < 1e-12 and abs(c[1] - 0.75) < 1e-12
+    n, world = 12, 3
+    bounds = [0, 3, 8, 12]
+    marks = torch.zeros((world, n), dtype=torch.uint8)
+    marks[0, [0, 1, 5, 9]] = 1      # rank 0 reads rows 0, 1 (own) and 5, 9 (halo)
+    marks[1, [2, 4, 5, 11]] = 1
+    marks[2, [0, 4, 9, 10]] = 1
+    m1, l1 = halo_masks(marks, bounds, 1)   # rank 1 owns rows 3..7; its peers in order: rank 0 (bit 0), rank 2 (bit 1)
+    assert m1.tolist() == [0, 2, 1, 0, 0]   # row 4 -> rank 2, row 5 -> rank 0
+    assert l1.tolist() == [0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1]
+    m0, l0 = halo_masks(marks, bounds, 0)   # peers: rank 1 (bit 0), rank 2 (bit 1)
+    assert m0.tolist() == [2, 0, 1] and l0.tolist() == [1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0]
+    m2, _ = halo_masks(marks, bounds, 2)    # rows 8..11; peers: rank 0 (bit 0), rank 1 (bit 1)
+    assert m2.tolist() == [0, 1, 0, 2]
