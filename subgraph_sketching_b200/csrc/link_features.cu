@@ -353,42 +353,209 @@ __device__ __forceinline__ const uint8_t *lk_table(const LinkArgs &a, int k1, in
     return a.peer_hop[k1][owner];
 }
 
+__device__ __forceinline__ uint4 lk_lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint2 lk_lds_u2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+// Per-lane slot of the batched tail: the raw statistics of ONE (link, combination) of the running batch
+struct LkSlot {
+    uint32_t lo, hi, match;   // fixed-point sum of 2^-r (two halves), matching MinHash slots
+    int zeros;                // empty registers of the union
+    float Sx;                 // >= 0: exact-path sum (some register > 28)
+};
+
+// all K^2 combinations of one link whose prepared records are in registers; lane (j, c) keeps combination c
 template <int K>
-__global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const LinkArgs a, const int tile, const int prefetch) {
+__device__ __forceinline__ void lk_combine(const RowRegsB *U, const RowRegsB *V, uint32_t big, int j, int my_j, int my_c,
+                                           LkSlot &sl) {
     constexpr int C = K * K;
-    constexpr int B = 32 / C;
-    constexpr int F = K * (K + 2);
     constexpr int EQW = (C + 3) / 4, NZW = (C + 2) / 3;
-    __shared__ float stage_all[8][B * F];
-    __shared__ float cards_all[8][B * 2 * K];  // cards of the batch's endpoints, fetched asynchronously at batch start
-    // endpoints of the current and the next tile of every warp (cp.async: no register staging, the load of the
-    // next tile -- a PCIe round trip when the link list is a pinned host buffer -- overlaps the current tile)
-    __shared__ __align__(16) longlong2 ids_all[8][2][LK_TILE_MAX];
+    const bool any_big = __any_sync(FULL, big != 0u);
+    const bool mine = (my_j == j);
+    const int my_slot = mine ? my_c : -1;  // combination this lane keeps for this link
+    uint32_t eq_pack[EQW] = {0}, nz_pack[NZW] = {0};
+#pragma unroll
+    for (int k1 = 0; k1 < K; ++k1) {
+#pragma unroll
+        for (int k2 = 0; k2 < K; ++k2) {
+            const int c = k1 * K + k2;
+            // mismatching slots: min(x ^ y, 1) summed (XOR + VIMNMX per slot, IADD3 for the sums)
+            const uint32_t ne = lk_nonzero(U[k1].mh.x ^ V[k2].mh.x) + lk_nonzero(U[k1].mh.y ^ V[k2].mh.y) +
+                                lk_nonzero(U[k1].mh.z ^ V[k2].mh.z) + lk_nonzero(U[k1].mh.w ^ V[k2].mh.w);
+            eq_pack[c / 4] += ne << (8 * (c % 4));  // MISmatches; turned into matches at extraction
+            nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
+        }
+    }
+    if (!any_big) {
+#pragma unroll
+        for (int k1 = 0; k1 < K; ++k1) {
+#pragma unroll
+            for (int k2 = 0; k2 < K; ++k2) {
+                const int c = k1 * K + k2;
+                const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
+                const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
+                const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_even(ox) + pow_sum_even(oy);
+                const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
+                const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
+                if (my_slot == c) { sl.lo = lo; sl.hi = hi; }
+            }
+        }
+    } else {  // rare: exact 128-bit path, combination by combination
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            const int k1 = c / K, k2 = c % K;
+            uint2 ue = make_uint2(0u, 0u), uo = ue, ve = ue, vo = ue;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k == k1) { ue = U[k].he; uo = U[k].ho; }
+                if (k == k2) { ve = V[k].he; vo = V[k].ho; }
+            }
+            uint64_t acc = 0;
+            int nz = 0, zeros;
+            acc_regs_word(__vmaxu2(ue.x, ve.x) | (__vmaxu2(uo.x, vo.x) << 8), acc, nz);
+            acc_regs_word(__vmaxu2(ue.y, ve.y) | (__vmaxu2(uo.y, vo.y) << 8), acc, nz);
+            unsigned __int128 tot = warp_total_units(acc, nz, zeros);
+            const float S = units_to_f32(tot);
+            if (my_slot == c) sl.Sx = S;
+        }
+    }
+    uint32_t eq_r[3] = {0, 0, 0}, nz_r[3] = {0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < EQW; ++w) eq_r[w] = __reduce_add_sync(FULL, eq_pack[w]);
+#pragma unroll
+    for (int w = 0; w < NZW; ++w) nz_r[w] = __reduce_add_sync(FULL, nz_pack[w]);
+    if (mine) {
+        const int nz_w = my_c / 3;
+        sl.match = 128u - (((uint32_t)lk_select3(my_c >> 2, (int)eq_r[0], (int)eq_r[1], (int)eq_r[2]) >> (8 * (my_c & 3))) & 0xffu);
+        sl.zeros = 256 - (int)(((uint32_t)lk_select3(nz_w, (int)nz_r[0], (int)nz_r[1], (int)nz_r[2]) >>
+                                (10 * (my_c - 3 * nz_w))) & 0x3ffu);
+    }
+}
+
+// batched tails + algebra + stores of the nb links [i0, i0 + nb); cards: the batch's cardinalities in shared memory,
+// link j at cards[j * 2K .. j * 2K + 2K) (u's K then v's K)
+template <int K>
+__device__ __forceinline__ void lk_finish_batch(const LinkArgs &a, const LkSlot &sl, int nb, int64_t i0, int lane,
+                                                const float *cards, float *stage) {
+    constexpr int C = K * K;
+    constexpr int F = K * (K + 2);
+    // ---- batched tails: lane (j, c) finishes combination c of link j
+    float my_inter = 0.f;
+    if (lane < nb * C) {
+        // lo < 2^21 and hi < 2^20 are exact in float32 and so is hi * 2^16: one rounding in the add gives the
+        // correctly rounded total
+        float S = sl.Sx;
+        if (S < 0.f) S = __fmul_rn(__fadd_rn(__fmul_rn((float)sl.hi, 65536.f), (float)sl.lo), 3.7252902984619140625e-09f);
+        my_inter = intersection_tail(a.h, sl.zeros, S, sl.match, 128);
+    }
+    if (a.inter && lane < nb * C) a.inter[i0 * C + lane] = my_inter;  // contiguous: consecutive links
+    if (a.features) {
+        // ---- batched algebra: lane j = link j of the batch
+        const int jj = lane < nb ? lane : 0;
+        float I[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, jj * C + c);
+        float cu[K], cv[K], f[F];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            cu[k] = cards[jj * 2 * K + k];
+            cv[k] = cards[jj * 2 * K + K + k];
+        }
+        feature_algebra<K>(I, cu, cv, f);
+        knockout_and_floor<K>(f, a.flags);
+        __syncwarp();
+        if (lane < nb) {
+#pragma unroll
+            for (int x = 0; x < F; ++x) stage[lane * F + x] = f[x];
+        }
+        __syncwarp();
+        for (int x = lane; x < nb * F; x += 32) a.features[i0 * F + x] = stage[x];
+    }
+}
+
+__device__ __forceinline__ void lk_cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// Shared memory of one warp (dynamic, carved by lk_smem_per_warp):
+//   ids    2 x tile x 16 B   endpoints of the current and the next tile (cp.async double buffer)
+//   recs   2K x 768 B        the records of the NEXT link, in flight while the current link is evaluated
+//   cards  2 x B x 2K floats cardinalities of the endpoints of the current and the next batch (arrive with the records)
+//   stage  B x F floats      feature transpose
+template <int K> struct LkSmem {
+    static constexpr int C = K * K, B = 32 / C, F = K * (K + 2);
+    static constexpr int IDS = 2 * LK_TILE_MAX * 16, RECS = 2 * K * 768, CARDS = 2 * B * 2 * K * 4, STAGE = B * F * 4;
+    static constexpr int PER_WARP = (IDS + RECS + CARDS + STAGE + 15) & ~15;
+};
+
+// One warp owns a tile of consecutive links.  Software pipeline per link (no registers spent on it):
+//     wait for the link's records in shared memory -> LDS + prepare -> request the NEXT link's records (cp.async)
+//     -> K^2 combinations from registers
+// so the DRAM (or NVLink, for rows held by another GPU) round trip of link j + 1 overlaps the ~800 instructions of
+// link j instead of stalling the warp in front of its first use (17 % of all stall samples before).  Along a run of
+// links with the same source only v's records move.
+template <int K>
+__global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const LinkArgs a, const int tile) {
+    typedef LkSmem<K> SM;
+    constexpr int C = SM::C, B = SM::B;
+    extern __shared__ __align__(16) uint8_t lk_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *stage = stage_all[warp];
+    uint8_t *mine_smem = lk_smem + warp * SM::PER_WARP;
+    longlong2 *ids_buf = reinterpret_cast<longlong2 *>(mine_smem);
+    const uint32_t recs = smem_u32(mine_smem + SM::IDS);
+    float *cards = reinterpret_cast<float *>(mine_smem + SM::IDS + SM::RECS);
+    float *stage = reinterpret_cast<float *>(mine_smem + SM::IDS + SM::RECS + SM::CARDS);
     const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
     const int n_tiles = (int)((a.n_links + tile - 1) / tile);  // the host keeps n_links / tile below 2^31
-    // which combination / batch slot this lane serves in the batched tail
-    const int my_j = lane / C;              // link of the batch (>= B for the idle lanes of K = 3)
+    const int my_j = lane / C;              // link of the batch this lane's tail slot belongs to (>= B: idle)
     const int my_c = lane - my_j * C;
+    const bool sharded = a.n_ranks > 1;
 
     auto fetch_ids = [&](int t, int buf) {
         const int64_t base = (int64_t)t * tile;
         const int cnt = (int)min((int64_t)tile, a.n_links - base);
         for (int x = lane; x < cnt; x += 32)
-            lk_cp_async16(smem_u32(&ids_all[warp][buf][x]), reinterpret_cast<const longlong2 *>(a.links) + base + x);
-        lk_cp_async_commit();
+            lk_cp_async16(smem_u32(ids_buf + buf * LK_TILE_MAX + x), reinterpret_cast<const longlong2 *>(a.links) + base + x);
     };
+    // request the records (and cardinalities) of link `li` of the tile; u's only when it differs from `u_prev`
+    auto request = [&](const longlong2 *ids, int li, int slot, int u_prev) {
+        const int2 e = reinterpret_cast<const int2 *>(ids + li)[0];
+        const int ow_u = sharded ? lk_owner(a, e.x) : 0, ow_v = sharded ? lk_owner(a, e.y) : 0;
+        const bool have_u = sharded ? (__ldg(a.local_rows + e.x) != 0) : true;
+        const bool have_v = sharded ? (__ldg(a.local_rows + e.y) != 0) : true;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (e.x != u_prev) {
+                const uint8_t *ru = lk_table(a, k + 1, K, ow_u, have_u) + (int64_t)e.x * a.stride[k + 1];
+                lk_cp_async16(recs + k * 768 + lane * 16, ru + lane * 16);
+                lk_cp_async8(recs + k * 768 + REC_MH + lane * 8, ru + REC_MH + lane * 8);
+            }
+            const uint8_t *rv = lk_table(a, k + 1, K, ow_v, have_v) + (int64_t)e.y * a.stride[k + 1];
+            lk_cp_async16(recs + (K + k) * 768 + lane * 16, rv + lane * 16);
+            lk_cp_async8(recs + (K + k) * 768 + REC_MH + lane * 8, rv + REC_MH + lane * 8);
+        }
+        if (a.features && lane < 2 * K) {
+            const int node = lane < K ? e.x : e.y;
+            lk_cp_async4(smem_u32(cards + slot * 2 * K + lane), a.cards + (int64_t)node * a.cards_stride + (lane < K ? lane : lane - K));
+        }
+    };
+
     int buf = 0;
     if (gwarp < n_tiles) fetch_ids(gwarp, 0);
-
     for (int t = gwarp; t < n_tiles; t += n_warps) {
         lk_cp_async_wait();
         __syncwarp();
         if (t + n_warps < n_tiles) fetch_ids(t + n_warps, buf ^ 1);
-        longlong2 *ids = ids_all[warp][buf];
+        longlong2 *ids = ids_buf + buf * LK_TILE_MAX;
         buf ^= 1;
         const int cnt = (int)min((int64_t)tile, a.n_links - (int64_t)t * tile);
         // bounds-check the tile's endpoints once (the reference would raise IndexError); from here on they are int32
@@ -400,167 +567,45 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
         RowRegsB U[K];
         uint32_t big_u = 0;
         int u_cur = -1;
-        for (int b0 = 0; b0 < cnt; b0 += B) {
+        request(ids, 0, 0, -1);
+        int half = 0;  // which half of `cards` the running batch uses
+        for (int b0 = 0; b0 < cnt; b0 += B, half ^= 1) {
             const int nb = min(B, cnt - b0);
-            // the cardinalities the algebra of this batch will need: in flight (no registers) during the K^2 merges,
-            // instead of a dependent DRAM round trip in front of every batch's algebra
-            if (a.features && lane < nb) {
-                const int2 ec = reinterpret_cast<const int2 *>(ids + b0 + lane)[0];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    lk_cp_async4(smem_u32(&cards_all[warp][lane * 2 * K + k]), a.cards + (int64_t)ec.x * a.cards_stride + k);
-                    lk_cp_async4(smem_u32(&cards_all[warp][lane * 2 * K + K + k]), a.cards + (int64_t)ec.y * a.cards_stride + k);
-                }
-            }
-            lk_cp_async_commit();
-            uint32_t my_lo = 0, my_hi = 0, my_match = 0;
-            int my_zeros = 0;
-            float my_Sx = -1.f;  // >= 0: exact-path sum (some register > 28)
+            LkSlot sl;
+            sl.lo = sl.hi = sl.match = 0u;
+            sl.zeros = 0;
+            sl.Sx = -1.f;
 #pragma unroll 1
             for (int j = 0; j < nb; ++j) {
-                const int2 e = reinterpret_cast<const int2 *>(ids + b0 + j)[0];  // broadcast read
-                const int u = e.x, v = e.y;
-                // pull the NEXT link's records into L2 while this one is evaluated (costs no registers): a warp has one
-                // link in flight, so without this every link pays a full DRAM round trip before its first instruction
-                if (prefetch && a.n_ranks <= 1 && b0 + j + 1 < cnt) {
-                    const int2 en = reinterpret_cast<const int2 *>(ids + b0 + j + 1)[0];
-#pragma unroll
-                    for (int x0 = 0; x0 < 12 * K; x0 += 32) {
-                        const int x = x0 + lane;
-                        const int rec = x / 6, line = x - rec * 6;       // 6 x 128-byte lines per record
-                        const int side = rec / K, k = rec - side * K;    // records 0..K-1: u, K..2K-1: v
-                        const int node = side ? en.y : en.x;
-                        if (x < 12 * K && (side || node != u)) {
-                            const uint8_t *base = k == 0 ? a.hop[1] : (k == 1 ? a.hop[2] : a.hop[3]);
-                            const int64_t strd = k == 0 ? a.stride[1] : (k == 1 ? a.stride[2] : a.stride[3]);
-                            lk_prefetch_l2(base + (int64_t)node * strd + line * 128);
-                        }
-                    }
-                }
-                const bool sharded = a.n_ranks > 1;
-                const int ow_v = sharded ? lk_owner(a, v) : 0;
-                const bool have_v = sharded ? (__ldg(a.local_rows + v) != 0) : true;
+                const int u = reinterpret_cast<const int2 *>(ids + b0 + j)[0].x;
+                lk_cp_async_wait();   // this link's records (and, long since, the next tile's ids)
+                __syncwarp();
                 if (u != u_cur) {  // warp-uniform: a run of links with the same source keeps u's prepared records
                     u_cur = u;
                     big_u = 0;
-                    const int ow = sharded ? lk_owner(a, u) : 0;
-                    const bool have = sharded ? (__ldg(a.local_rows + u) != 0) : true;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const uint8_t *ru = lk_table(a, k + 1, K, ow, have) + (int64_t)u * a.stride[k + 1];
-                        const uint4 m = ld_nc_u4(ru + lane * 16);
-                        const uint2 h = ld_nc_u2(ru + REC_MH + lane * 8);
-                        prep_row_b(U[k], m, h, big_u);
-                    }
+                    for (int k = 0; k < K; ++k)
+                        prep_row_b(U[k], lk_lds_u4(recs + k * 768 + lane * 16), lk_lds_u2(recs + k * 768 + REC_MH + lane * 8), big_u);
                 }
+                // v's raw words leave shared memory first (18 registers), then the buffer is free and the NEXT link's
+                // request goes out before anything is computed
+                uint4 mv[K];
+                uint2 hv[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    mv[k] = lk_lds_u4(recs + (K + k) * 768 + lane * 16);
+                    hv[k] = lk_lds_u2(recs + (K + k) * 768 + REC_MH + lane * 8);
+                }
+                __syncwarp();  // every lane has its copy: the buffer may be refilled
+                if (b0 + j + 1 < cnt) request(ids, b0 + j + 1, (j + 1 < nb) ? half * B + j + 1 : (half ^ 1) * B, u);
                 RowRegsB V[K];
                 uint32_t big = big_u;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const uint8_t *rv = lk_table(a, k + 1, K, ow_v, have_v) + (int64_t)v * a.stride[k + 1];
-                    const uint4 m = ld_nc_u4(rv + lane * 16);
-                    const uint2 h = ld_nc_u2(rv + REC_MH + lane * 8);
-                    prep_row_b(V[k], m, h, big);
-                }
-                const bool any_big = __any_sync(FULL, big != 0u);
-                const bool mine = (my_j == j);
-                const int my_slot = mine ? my_c : -1;  // combination this lane keeps for this link
-
-                uint32_t eq_pack[EQW] = {0}, nz_pack[NZW] = {0};
-#pragma unroll
-                for (int k1 = 0; k1 < K; ++k1) {
-#pragma unroll
-                    for (int k2 = 0; k2 < K; ++k2) {
-                        const int c = k1 * K + k2;
-                        // mismatching slots: min(x ^ y, 1) summed (XOR + VIMNMX per slot, IADD3 for the sums)
-                        const uint32_t ne = lk_nonzero(U[k1].mh.x ^ V[k2].mh.x) + lk_nonzero(U[k1].mh.y ^ V[k2].mh.y) +
-                                            lk_nonzero(U[k1].mh.z ^ V[k2].mh.z) + lk_nonzero(U[k1].mh.w ^ V[k2].mh.w);
-                        eq_pack[c / 4] += ne << (8 * (c % 4));  // MISmatches; turned into matches at extraction
-                        nz_pack[c / 3] += (uint32_t)__popc(U[k1].nz | V[k2].nz) << (10 * (c % 3));
-                    }
-                }
-                if (!any_big) {
-#pragma unroll
-                    for (int k1 = 0; k1 < K; ++k1) {
-#pragma unroll
-                        for (int k2 = 0; k2 < K; ++k2) {
-                            const int c = k1 * K + k2;
-                            const uint32_t ex = __vmaxu2(U[k1].he.x, V[k2].he.x), ey = __vmaxu2(U[k1].he.y, V[k2].he.y);
-                            const uint32_t ox = __vmaxu2(U[k1].ho.x, V[k2].ho.x), oy = __vmaxu2(U[k1].ho.y, V[k2].ho.y);
-                            const uint32_t acc = pow_sum_even(ex) + pow_sum_even(ey) + pow_sum_even(ox) + pow_sum_even(oy);
-                            const uint32_t lo = __reduce_add_sync(FULL, acc & 0xffffu);
-                            const uint32_t hi = __reduce_add_sync(FULL, acc >> 16);
-                            if (my_slot == c) { my_lo = lo; my_hi = hi; }
-                        }
-                    }
-                } else {  // rare: exact 128-bit path, combination by combination
-#pragma unroll 1
-                    for (int c = 0; c < C; ++c) {
-                        const int k1 = c / K, k2 = c % K;
-                        uint2 ue = make_uint2(0u, 0u), uo = ue, ve = ue, vo = ue;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            if (k == k1) { ue = U[k].he; uo = U[k].ho; }
-                            if (k == k2) { ve = V[k].he; vo = V[k].ho; }
-                        }
-                        uint64_t acc = 0;
-                        int nz = 0, zeros;
-                        acc_regs_word(__vmaxu2(ue.x, ve.x) | (__vmaxu2(uo.x, vo.x) << 8), acc, nz);
-                        acc_regs_word(__vmaxu2(ue.y, ve.y) | (__vmaxu2(uo.y, vo.y) << 8), acc, nz);
-                        unsigned __int128 tot = warp_total_units(acc, nz, zeros);
-                        const float S = units_to_f32(tot);
-                        if (my_slot == c) my_Sx = S;
-                    }
-                }
-                uint32_t eq_r[3] = {0, 0, 0}, nz_r[3] = {0, 0, 0};
-#pragma unroll
-                for (int w = 0; w < EQW; ++w) eq_r[w] = __reduce_add_sync(FULL, eq_pack[w]);
-#pragma unroll
-                for (int w = 0; w < NZW; ++w) nz_r[w] = __reduce_add_sync(FULL, nz_pack[w]);
-                if (mine) {
-                    const int nz_w = my_c / 3;
-                    my_match = 128u - (((uint32_t)lk_select3(my_c >> 2, (int)eq_r[0], (int)eq_r[1], (int)eq_r[2]) >> (8 * (my_c & 3))) & 0xffu);
-                    my_zeros = 256 - (int)(((uint32_t)lk_select3(nz_w, (int)nz_r[0], (int)nz_r[1], (int)nz_r[2]) >>
-                                            (10 * (my_c - 3 * nz_w))) & 0x3ffu);
-                }
+                for (int k = 0; k < K; ++k) prep_row_b(V[k], mv[k], hv[k], big);
+                lk_combine<K>(U, V, big, j, my_j, my_c, sl);
             }
-            // ---- batched tails: lane (j, c) finishes combination c of link j
-            float my_inter = 0.f;
-            if (lane < nb * C) {
-                // lo < 2^21 and hi < 2^20 are exact in float32 and so is hi * 2^16: one rounding in the add gives the
-                // correctly rounded total
-                float S = my_Sx;
-                if (S < 0.f)
-                    S = __fmul_rn(__fadd_rn(__fmul_rn((float)my_hi, 65536.f), (float)my_lo), 3.7252902984619140625e-09f);
-                my_inter = intersection_tail(a.h, my_zeros, S, my_match, 128);
-            }
-            const int64_t i0 = (int64_t)t * tile + b0;
-            if (a.inter && lane < nb * C) a.inter[i0 * C + lane] = my_inter;  // contiguous: consecutive links
-            if (a.features) {
-                // ---- batched algebra: lane j = link j of the batch
-                const int jj = lane < nb ? lane : 0;
-                float I[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) I[c] = __shfl_sync(FULL, my_inter, jj * C + c);
-                // everything but the next tile's ids (the youngest group, if one is in flight) has landed
-                lk_cp_async_wait();
-                __syncwarp();
-                float cu[K], cv[K], f[F];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    cu[k] = cards_all[warp][jj * 2 * K + k];
-                    cv[k] = cards_all[warp][jj * 2 * K + K + k];
-                }
-                feature_algebra<K>(I, cu, cv, f);
-                knockout_and_floor<K>(f, a.flags);
-                __syncwarp();
-                if (lane < nb) {
-#pragma unroll
-                    for (int x = 0; x < F; ++x) stage[lane * F + x] = f[x];
-                }
-                __syncwarp();
-                for (int x = lane; x < nb * F; x += 32) a.features[i0 * F + x] = stage[x];
-            }
+            // (the cardinalities of the NEXT batch's first link are already landing in the other half of `cards`)
+            lk_finish_batch<K>(a, sl, nb, (int64_t)t * tile + b0, lane, cards + half * B * 2 * K, stage);
         }
     }
 }
@@ -600,16 +645,6 @@ __device__ __forceinline__ void lk_gather4(uint32_t dst, const CUtensorMap *tmap
         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
         : "memory");
-}
-__device__ __forceinline__ uint4 lk_lds_u4(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ uint2 lk_lds_u2(uint32_t addr) {
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
-    return r;
 }
 
 constexpr int LK_WARPS = 4;
@@ -766,10 +801,19 @@ static EncodeTiledFn lk_encode_fn() {
 // which front end.  Measured on B200 (R-MAT 24, K=3, 20 M links): LDG 27.8 ms, TMA pairs 37.2 ms -- the kernel is
 // instruction-bound (~900 warp instructions per link) and the TMA stages cap residency at 12 warps / SM, so
 // hiding the load latency does not pay for the lost issue slots.  LDG is the default; SS_B200_LINKS=tma opts in.
-// SS_B200_LINKS=ldg: the round-1 kernel (one link per warp at a time, tails per link)
-static bool want_per_link_kernel() {
+// which kernel evaluates unsharded links (measured on B200, R-MAT 24, 20 M links -- profiles/r02_link_features.txt):
+//   K = 3: the per-link kernel (22.3 ms random) beats the batched one (24.0-25.3 ms) although the latter executes
+//          16 % fewer instructions: both are bound by the ALU pipe (LOP3 / SHF / IADD3 / VIMNMX issue every other
+//          cycle per scheduler) and the batched kernel's extra shared-memory traffic costs more than its shorter
+//          tails save; on source-grouped lists the two are equal (22.2 vs 22.5 ms)
+//   K <= 2: the batched kernel wins (13.9 vs 14.8 ms random, 11.7 vs 14.8 ms grouped)
+// SS_B200_LINKS=ldg / batched / tma overrides; sharded tables are always read by the batched kernel (its software
+// pipeline also hides the NVLink round trip of records held by another GPU).
+static bool want_per_link_kernel(int K, bool sharded) {
     const char *e = getenv("SS_B200_LINKS");
-    return e && e[0] == 'l';
+    if (e && e[0] == 'l') return true;
+    if (e && e[0] == 'b') return false;
+    return K == 3 && !sharded;
 }
 
 static bool want_tma_links() {
@@ -810,7 +854,7 @@ static int launch_links(const LinkArgs &a, const int64_t *hop_rows, bool fast, c
         int64_t resident = (int64_t)per_sm * sm_count();
         k<<<(int)(want < resident ? want : resident), LK_WARPS * 32, smem, st>>>(a, maps);
         SS_LAUNCH_CHECK("link_features_tma_kernel");
-    } else if (fast && want_per_link_kernel()) {
+    } else if (fast && want_per_link_kernel(K, a.n_ranks > 1)) {
         link_features_kernel<K><<<grid, 256, 0, st>>>(a);
         SS_LAUNCH_CHECK("link_features_kernel");
     } else if (fast) {
@@ -828,9 +872,10 @@ static int launch_links(const LinkArgs &a, const int64_t *hop_rows, bool fast, c
         const int64_t n_tiles = (a.n_links + tile - 1) / tile;
         int64_t bl = (n_tiles + 7) / 8;
         int64_t cap_b = (int64_t)sm_count() * 3;
-        int prefetch = 0;  // measured: prefetch.global.L2 of the next link's 36 lines costs more than it hides (27.2 vs 23.5 ms)
-        if (const char *e = getenv("SS_B200_LINK_PREFETCH")) prefetch = atoi(e);  // tuning knob
-        link_features_batched_kernel<K><<<(int)(bl < cap_b ? bl : cap_b), 256, 0, st>>>(a, (int)tile, prefetch);
+        auto k = link_features_batched_kernel<K>;
+        const size_t smem = 8 * (size_t)LkSmem<K>::PER_WARP;
+        SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(int)(bl < cap_b ? bl : cap_b), 256, smem, st>>>(a, (int)tile);
         SS_LAUNCH_CHECK("link_features_batched_kernel");
     } else {
         link_features_generic_kernel<K><<<grid, 256, 0, st>>>(a);
@@ -896,7 +941,7 @@ int ss_link_features_sharded(const int64_t *links, int64_t n_links, const ss_hop
         SS_REQUIRE(shard->n_ranks <= SS_MAX_PEERS + 1 && shard->rank >= 0 && shard->rank < shard->n_ranks,
                    "bad rank / world size in ss_shard_view");
         SS_REQUIRE(shard->local_rows, "ss_shard_view.local_rows is null");
-        SS_REQUIRE(!ss::want_per_link_kernel() && !ss::want_tma_links(), "sharded tables are read by the batched kernel only");
+        SS_REQUIRE(!ss::want_per_link_kernel(max_hops, true) && !ss::want_tma_links(), "sharded tables are read by the batched kernel only");
         a.n_ranks = shard->n_ranks;
         a.rank = shard->rank;
         a.last_hop_own_only = shard->last_hop_own_only;

@@ -160,3 +160,25 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
                 assert '/root/reference' not in text.replace('/root/reference/src', 'REFDOC'), f
+
+
+def test_packaged_hllpp_tables_warn_and_are_labelled(monkeypatch):
+    """without datasketch the Monte-Carlo substitute tables are used: loudly (RuntimeWarning) and labelled on the
+    engine; explicit tables are labelled as the caller's"""
+    import warnings
+    import subgraph_sketching_b200.hashing as H
+    try:
+        import datasketch  # noqa: F401
+        return  # the real constants are importable here: nothing to warn about
+    except ImportError:
+        pass
+    monkeypatch.setattr(H, '_warned_tables', set())
+    monkeypatch.delenv('SS_B200_HLLPP_TABLES', raising=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        eh = ssb.ElphHashes(make_args())
+    assert any(issubclass(x.category, RuntimeWarning) and 'Monte-Carlo' in str(x.message) for x in w)
+    assert eh.hll_tables_source == 'packaged-monte-carlo'
+    thr, est, bias = H.hllpp_tables(8)
+    eh2 = ssb.ElphHashes(make_args(), hll_tables=(thr, est, bias))
+    assert eh2.hll_tables_source == 'caller'

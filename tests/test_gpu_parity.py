@@ -235,6 +235,19 @@ def test_small_helpers():
         eh.jaccard(a, b[:10])
 
 
+def test_cards_with_fewer_rows_than_the_tables_raise():
+    """mismatched caches (cards shorter than the hash tables): IndexError like the reference's cards[links[:, 0]],
+    never an out-of-bounds read"""
+    n = 500
+    ei = rmat_edges(9, 8, 2).to(DEV)
+    eh = ssb.ElphHashes(make_args(2))
+    tables, cards = eh.build_hash_tables(n, ei)
+    links = torch.tensor([[0, 1], [n - 1, 2]], device=DEV)
+    with pytest.raises(IndexError):
+        eh.get_subgraph_features(links, tables, cards[:n - 10])
+    assert eh.get_subgraph_features(links, tables, cards).shape == (2, 8)
+
+
 def test_feature_api_contract():
     """ports of test_get_subgraph_features (test/test_hashing.py:179-194) and
     test_get_subgraph_features_batched (test/test_elph_datasets.py:69-91)"""
@@ -447,7 +460,7 @@ def test_link_feature_front_ends_agree(monkeypatch):
                 ib = eh._get_intersections(lk, tables)
                 assert torch.equal(a, b), (K, L)
                 assert all(torch.equal(ia[k], ib[k]) for k in ia)
-                monkeypatch.delenv('SS_B200_LINKS')
+                monkeypatch.setenv('SS_B200_LINKS', 'batched')
                 for tile in (None, 3, 8, 24, 32, 96):
                     if tile is None:
                         monkeypatch.delenv('SS_B200_LINK_TILE', raising=False)
@@ -458,7 +471,11 @@ def test_link_feature_front_ends_agree(monkeypatch):
                     assert torch.equal(a, c), (K, L, tile)
                     assert all(torch.equal(ia[k], ic[k]) for k in ia), (K, L, tile)
                 monkeypatch.delenv('SS_B200_LINK_TILE', raising=False)
+                monkeypatch.delenv('SS_B200_LINKS')
+                d = eh.get_subgraph_features(lk, tables, cards)   # the default choice for this K
+                assert torch.equal(a, d), (K, L)
     # out-of-range endpoints are flagged by the batched kernel too
+    monkeypatch.setenv('SS_B200_LINKS', 'batched')
     with pytest.raises(IndexError):
         eh.get_subgraph_features(torch.tensor([[0, 1], [2, n]], device=DEV), tables, cards)
     with pytest.raises(IndexError):
@@ -665,7 +682,18 @@ def test_cache_round_trip_in_reference_formats(tmp_path):
     hashes = torch.load(root + 'train_3hop_hashcache.pt')            # the reference's plain mapping of CPU tensors
     assert sorted(hashes.keys()) == [0, 1, 2, 3] and hashes[2]['minhash'].dtype == torch.int64
     assert np.array_equal(hashes[3]['hll'].numpy(), blob['hll_3'])
-    assert np.array_equal(torch.load(root + 'train_3hop_cardcache.pt').numpy(), eh.build_hash_tables(300, ei)[1].numpy())
+    saved_cards = torch.load(root + 'train_3hop_cardcache.pt', map_location='cpu', weights_only=True)
+    assert np.array_equal(saved_cards.numpy(), eh.build_hash_tables(300, ei)[1].numpy())
+    # the cardinalities handed to a CPU caller carry nothing of the engine: a plain CPU tensor with an empty __dict__
+    # (torch.save pickles attributes; an embedded device twin would bloat the cache and pin it to one GPU)
+    host_cards = eh.build_hash_tables(300, ei)[1]
+    assert not host_cards.is_cuda and host_cards.__dict__ == {} and saved_cards.__dict__ == {}
+    import os as _os
+    assert _os.path.getsize(root + 'train_3hop_cardcache.pt') < 300 * 3 * 4 + 4096
+    # ... and the twin that spares get_subgraph_features the re-upload is dropped with the tensor / on modification
+    assert eh._twin_of(host_cards, torch.device(DEV)) is not None
+    host_cards[0, 0] += 1.0
+    assert eh._twin_of(host_cards, torch.device(DEV)) is None
     f2 = cache.preprocess_subgraph_features(eh, root, 'train', links, ei, 300, load_hashes=True,
                                             cache_subgraph_features=True)     # from the hash cache
     assert torch.equal(f1, f2)

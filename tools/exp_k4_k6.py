@@ -60,7 +60,7 @@ for K in (3, 2):
             if mode == 'ldg':
                 os.environ['SS_B200_LINKS'] = 'ldg'
             else:
-                os.environ.pop('SS_B200_LINKS', None)
+                os.environ['SS_B200_LINKS'] = 'batched'
             f = eh.get_subgraph_features(lk, tables, cards)
             if name not in ref:
                 ref[name] = f
