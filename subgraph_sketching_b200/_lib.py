@@ -85,6 +85,7 @@ SIGNATURES = {
     'ss_csr_sorted_finish_rows': (c_int, [c_i64, c_i64, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'ss_csr_sorted_bounds': (c_int, [c_ptr, c_i64, c_i64, ctypes.c_double, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_mark_rows': (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    'ss_halo_from_csr': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_csr_bin_workspace_bytes': (c_i64, []),
     'ss_csr_bin_edges': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                  c_ptr]),
@@ -140,7 +141,7 @@ def _load():
 # that return early on empty input are counted by the caller's own bookkeeping
 KERNELS_PER_CALL = {
     'ss_init_records': 1, 'ss_pack_records': 1, 'ss_unpack_records': 1, 'ss_csr_rowptr': 4, 'ss_csr_degree_chunk': 1, 'ss_csr_rowptr_finish': 3, 'ss_csr_fill': 2, 'ss_csr_bin_edges': 1, 'ss_csr_sorted_chunk': 1, 'ss_csr_sorted_finish': 1, 'ss_csr_sorted_chunk_rows': 1, 'ss_csr_sorted_finish_rows': 1,
-    'ss_csr_sorted_bounds': 1, 'ss_mark_rows': 1, 'ss_link_features_sharded': 1,
+    'ss_csr_sorted_bounds': 1, 'ss_mark_rows': 1, 'ss_halo_from_csr': 1, 'ss_link_features_sharded': 1,
     'ss_khop_merge': 2, 'ss_khop_merge_peers': 2, 'ss_khop_merge_ex': 2, 'ss_pack_records_ex': 1, 'ss_unpack_records_ex': 1,
     'ss_csr_build_nosync': 8, 'ss_i64_differs': 1, 'ss_prop_min_i64': 1, 'ss_prop_min_i64_guarded': 1, 'ss_prop_max_i8': 1, 'ss_hll_count': 1, 'ss_estimate_bias': 1,
     'ss_jaccard_i64': 1, 'ss_max_i8': 1, 'ss_link_features': 1, 'ss_col_sums': 1, 'ss_common_neighbour_scores': 1,

@@ -506,19 +506,30 @@ __global__ void __launch_bounds__(256) sorted_csr_finish_kernel(int64_t n_edges,
 }
 
 // cost-balanced row blocks of a key-ordered list without a histogram: cost(r) = (#edges with key < r) + row_cost * r,
-// cut at the cumulative shares cum[q]; one thread per cut, nested binary searches (key may be a pinned host pointer)
-__global__ void sorted_bounds_kernel(const int64_t *__restrict__ key, int64_t n_edges, int64_t n_rows, double row_cost,
-                                     const double *__restrict__ cum, int n_cuts, int64_t *bounds, int64_t *edge_off) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    auto lower = [&](int64_t r) {  // first e with key[e] >= r
-        int64_t lo = 0, hi = n_edges;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (key[mid] < r) lo = mid + 1; else hi = mid;
+// cut at the cumulative shares cum[q]; one WARP per cut, binary search over rows with a 32-ary search over the list
+// inside (key may be a pinned host pointer: ~150 dependent round trips per cut instead of ~700)
+__global__ void __launch_bounds__(256) sorted_bounds_kernel(const int64_t *__restrict__ key, int64_t n_edges, int64_t n_rows,
+                                                             double row_cost, const double *__restrict__ cum, int n_cuts,
+                                                             int64_t *bounds, int64_t *edge_off) {
+    const int lane = threadIdx.x & 31;
+    const int q = threadIdx.x >> 5;
+    auto lower = [&](int64_t r) {  // first e with key[e] >= r  (warp-cooperative; identical result on every lane)
+        int64_t lo = 0, hi = n_edges;  // invariant: key[lo - 1] < r <= key[hi]
+        while (hi - lo > 0) {
+            const int64_t span = hi - lo;
+            const int64_t step = (span + 32) / 33;  // 32 probes cut the span into 33 pieces
+            const int64_t pos = lo + (int64_t)(lane + 1) * step - 1;
+            const bool lt = pos < hi ? (key[pos] < r) : false;
+            const unsigned m = __ballot_sync(FULL, lt);
+            const int n_lt = __popc(m);  // probes are ordered: the first n_lt of them are < r
+            const int64_t new_lo = n_lt ? min(lo + (int64_t)n_lt * step, hi) : lo;
+            const int64_t new_hi = n_lt < 32 ? min(lo + (int64_t)(n_lt + 1) * step - 1, hi) : hi;
+            lo = new_lo;
+            hi = new_hi;
         }
         return lo;
     };
-    if (q == 0) { bounds[0] = 0; edge_off[0] = 0; bounds[n_cuts + 1] = n_rows; edge_off[n_cuts + 1] = n_edges; }
+    if (threadIdx.x == 0) { bounds[0] = 0; edge_off[0] = 0; bounds[n_cuts + 1] = n_rows; edge_off[n_cuts + 1] = n_edges; }
     if (q >= n_cuts) return;
     const double total = (double)n_edges + row_cost * (double)n_rows;
     const double target = cum[q] * total;
@@ -527,8 +538,39 @@ __global__ void sorted_bounds_kernel(const int64_t *__restrict__ key, int64_t n_
         const int64_t mid = (lo + hi) >> 1;
         if ((double)lower(mid) + row_cost * (double)mid < target) lo = mid + 1; else hi = mid;
     }
-    bounds[q + 1] = lo;
-    edge_off[q + 1] = lower(lo);
+    const int64_t e = lower(lo);
+    if (lane == 0) {
+        bounds[q + 1] = lo;
+        edge_off[q + 1] = e;
+    }
+}
+
+// halo of a SYMMETRIC graph from the owner's own CSR rows (no exchange): row r is read by rank q exactly when r has an
+// in-neighbour owned by q, so peer_mask[r] = OR over r's neighbours c of bit(position of owner(c) among the other
+// ranks); and every neighbour c is a row this rank reads: mark[c] = 1.  One warp per row.
+__global__ void __launch_bounds__(256) halo_from_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                                             int64_t n_rows, const int64_t *__restrict__ bounds, int n_ranks, int rank,
+                                                             uint8_t *__restrict__ peer_mask, uint8_t *__restrict__ mark) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int b[SS_MAX_PEERS + 1];  // b[q - 1] = first row of rank q (registers: the loops below are fully unrolled)
+#pragma unroll
+    for (int q = 1; q <= SS_MAX_PEERS; ++q) b[q - 1] = q < n_ranks ? (int)bounds[q] : 0x7fffffff;
+    for (int64_t r = gwarp; r < n_rows; r += n_warps) {
+        const int64_t s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+        unsigned bits = 0;
+        for (int64_t x = s + lane; x < e; x += 32) {
+            const int c = __ldg(colidx + x);
+            if (mark[c] == 0) mark[c] = 1;  // test first: a row is read by many lists but marked once
+            int o = 0;
+#pragma unroll
+            for (int q = 0; q < SS_MAX_PEERS; ++q) o += (c >= b[q]) ? 1 : 0;
+            if (o != rank) bits |= 1u << (o < rank ? o : o - 1);
+        }
+        bits = __reduce_or_sync(FULL, bits);
+        if (lane == 0) peer_mask[r] = (uint8_t)bits;
+    }
 }
 
 // mark[colidx[e]] = 1: the rows a rank's neighbour lists read (its halo + own rows), for the halo push of the
@@ -725,9 +767,23 @@ int ss_csr_sorted_bounds(const int64_t *key, int64_t n_edges, int64_t n_rows, do
     SS_REQUIRE(n_edges >= 0 && n_rows >= 0 && n_cuts >= 0 && n_cuts <= SS_MAX_PEERS, "bad sizes passed to ss_csr_sorted_bounds");
     SS_REQUIRE(bounds_out && edge_offsets_out && (n_cuts == 0 || cum_shares) && (n_edges == 0 || key),
                "null pointer passed to ss_csr_sorted_bounds");
-    ss::sorted_bounds_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(key, n_edges, n_rows, row_cost, cum_shares, n_cuts, bounds_out,
-                                                               edge_offsets_out);
+    ss::sorted_bounds_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(key, n_edges, n_rows, row_cost, cum_shares, n_cuts, bounds_out,
+                                                                edge_offsets_out);
     SS_LAUNCH_CHECK("sorted_bounds_kernel");
+    return SS_OK;
+}
+
+int ss_halo_from_csr(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *bounds, int n_ranks, int rank,
+                     uint8_t *peer_mask_out, uint8_t *mark_out, ss_stream_t stream) {
+    SS_REQUIRE(n_rows >= 0 && n_ranks >= 1 && n_ranks <= SS_MAX_PEERS + 1 && rank >= 0 && rank < n_ranks,
+               "bad sizes passed to ss_halo_from_csr");
+    if (n_rows == 0) return SS_OK;
+    SS_REQUIRE(rowptr && colidx && bounds && peer_mask_out && mark_out, "null pointer passed to ss_halo_from_csr");
+    int64_t blocks = (n_rows + 7) / 8;
+    int64_t cap = (int64_t)ss::sm_count() * 16;
+    ss::halo_from_csr_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        rowptr, colidx, n_rows, bounds, n_ranks, rank, peer_mask_out, mark_out);
+    SS_LAUNCH_CHECK("halo_from_csr_kernel");
     return SS_OK;
 }
 

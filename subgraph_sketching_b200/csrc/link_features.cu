@@ -353,6 +353,30 @@ __device__ __forceinline__ const uint8_t *lk_table(const LinkArgs &a, int k1, in
     return a.peer_hop[k1][owner];
 }
 
+__device__ __forceinline__ void lk_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void lk_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ uint4 lk_lds_u4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -489,10 +513,12 @@ __device__ __forceinline__ void lk_cp_async8(uint32_t dst, const void *src) {
 //   recs   2K x 768 B        the records of the NEXT link, in flight while the current link is evaluated
 //   cards  2 x B x 2K floats cardinalities of the endpoints of the current and the next batch (arrive with the records)
 //   stage  B x F floats      feature transpose
+//   bar    one mbarrier      transaction barrier of the record copies
 template <int K> struct LkSmem {
     static constexpr int C = K * K, B = 32 / C, F = K * (K + 2);
     static constexpr int IDS = 2 * LK_TILE_MAX * 16, RECS = 2 * K * 768, CARDS = 2 * B * 2 * K * 4, STAGE = B * F * 4;
-    static constexpr int PER_WARP = (IDS + RECS + CARDS + STAGE + 15) & ~15;
+    static constexpr int BAR = 16;  // one mbarrier: completion of the bulk copies of a link's records
+    static constexpr int PER_WARP = (IDS + RECS + CARDS + STAGE + BAR + 15) & ~15;
 };
 
 // One warp owns a tile of consecutive links.  Software pipeline per link (no registers spent on it):
@@ -513,6 +539,13 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
     const uint32_t recs = smem_u32(mine_smem + SM::IDS);
     float *cards = reinterpret_cast<float *>(mine_smem + SM::IDS + SM::RECS);
     float *stage = reinterpret_cast<float *>(mine_smem + SM::IDS + SM::RECS + SM::CARDS);
+    const uint32_t bar = smem_u32(mine_smem + ((SM::IDS + SM::RECS + SM::CARDS + SM::STAGE + 15) & ~15));
+    if (lane == 0) {
+        lk_mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t bar_parity = 0;
     const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
     const int n_tiles = (int)((a.n_links + tile - 1) / tile);  // the host keeps n_links / tile below 2^31
@@ -532,16 +565,20 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
         const int ow_u = sharded ? lk_owner(a, e.x) : 0, ow_v = sharded ? lk_owner(a, e.y) : 0;
         const bool have_u = sharded ? (__ldg(a.local_rows + e.x) != 0) : true;
         const bool have_v = sharded ? (__ldg(a.local_rows + e.y) != 0) : true;
+        // ONE bulk copy (cp.async.bulk, SASS UBLKCP) per 768-byte record, issued by lane 0, completion counted in bytes on
+        // the warp's mbarrier: a record held by another GPU crosses NVLink as a few large read requests instead of 48
+        // sector-sized ones (per-lane 16-byte loads reached only ~260 GB/s of NVLink read rate)
+        if (lane == 0) {
+            lk_mbar_expect(bar, (uint32_t)((e.x != u_prev ? 2 * K : K) * 768));
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (e.x != u_prev) {
-                const uint8_t *ru = lk_table(a, k + 1, K, ow_u, have_u) + (int64_t)e.x * a.stride[k + 1];
-                lk_cp_async16(recs + k * 768 + lane * 16, ru + lane * 16);
-                lk_cp_async8(recs + k * 768 + REC_MH + lane * 8, ru + REC_MH + lane * 8);
+            for (int k = 0; k < K; ++k) {
+                if (e.x != u_prev) {
+                    const uint8_t *ru = lk_table(a, k + 1, K, ow_u, have_u) + (int64_t)e.x * a.stride[k + 1];
+                    lk_bulk_g2s(recs + k * 768, ru, 768, bar);
+                }
+                const uint8_t *rv = lk_table(a, k + 1, K, ow_v, have_v) + (int64_t)e.y * a.stride[k + 1];
+                lk_bulk_g2s(recs + (K + k) * 768, rv, 768, bar);
             }
-            const uint8_t *rv = lk_table(a, k + 1, K, ow_v, have_v) + (int64_t)e.y * a.stride[k + 1];
-            lk_cp_async16(recs + (K + k) * 768 + lane * 16, rv + lane * 16);
-            lk_cp_async8(recs + (K + k) * 768 + REC_MH + lane * 8, rv + REC_MH + lane * 8);
         }
         if (a.features && lane < 2 * K) {
             const int node = lane < K ? e.x : e.y;
@@ -578,8 +615,9 @@ __global__ void __launch_bounds__(256, 3) link_features_batched_kernel(const Lin
 #pragma unroll 1
             for (int j = 0; j < nb; ++j) {
                 const int u = reinterpret_cast<const int2 *>(ids + b0 + j)[0].x;
-                lk_cp_async_wait();   // this link's records (and, long since, the next tile's ids)
-                __syncwarp();
+                lk_cp_async_wait();   // this link's cardinalities (and, long since, the next tile's ids)
+                lk_mbar_wait(bar, bar_parity);  // ... and its records
+                bar_parity ^= 1u;
                 if (u != u_cur) {  // warp-uniform: a run of links with the same source keeps u's prepared records
                     u_cur = u;
                     big_u = 0;
@@ -619,25 +657,6 @@ struct LinkMaps {
     CUtensorMap m[3];
 };
 
-__device__ __forceinline__ void lk_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void lk_mbar_expect(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void lk_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
 __device__ __forceinline__ void lk_gather4(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int r0, int r1, int r2,
                                            int r3) {
     asm volatile(

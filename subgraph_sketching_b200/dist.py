@@ -159,6 +159,7 @@ class ShardedElphHashes(object):
         self.exchange_error = None
         self.csr_path = None    # 'streaming' | 'histogram' (which CSR build the last call took)
         self._halo_mask = None
+        self._fp_keys = None
         if self.world_size == 1 or self.world_size - 1 > 7:
             self.exchange = 'nccl'
 
@@ -207,6 +208,11 @@ class ShardedElphHashes(object):
         G, r = self.world_size, self.rank
         n_edges = ei.shape[1]
         st = _stream_ptr(device)
+        if self._fp_keys is None:
+            # the fingerprints of all slices are summed: every rank must hash with the SAME (rank 0's random) keys
+            k = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in _FP_KEYS], dtype=torch.int64, device=device)
+            dist.broadcast(k, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            self._fp_keys = tuple(int(v) & ((1 << 64) - 1) for v in k.tolist())
         cum = torch.tensor(cumulative_shares(G, self.shares) or [0.5], dtype=torch.float64, device=device)
         cuts = torch.empty(2 * (G + 1), dtype=torch.int64, device=device)
         row_cost = 1.0 + default_row_weight(G, self.exchange)  # + 1: every row carries its self loop
@@ -226,8 +232,8 @@ class ShardedElphHashes(object):
         carry = torch.zeros(2, dtype=torch.int64, device=device)
 
         def chunk(k_ptr, v_ptr, count, e_base):
-            check(lib.ss_csr_sorted_chunk_rows(k_ptr, v_ptr, count, e_base, e_lo, lo, rows, 1, cap, _FP_KEYS[0],
-                                               _FP_KEYS[1], _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
+            check(lib.ss_csr_sorted_chunk_rows(k_ptr, v_ptr, count, e_base, e_lo, lo, rows, 1, cap, self._fp_keys[0],
+                                               self._fp_keys[1], _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
                                                _stream_ptr(device)), 'ss_csr_sorted_chunk_rows')
 
         ring = None
@@ -253,6 +259,8 @@ class ShardedElphHashes(object):
         del ring
         max_id, min_id = s[0], s[3]
         ok = s[8] == 0 and s[10] == 0 and (s[4], s[5]) == (s[6], s[7]) and max_id < num_nodes and (n_edges == 0 or min_id >= 0)
+        if _env_int('SS_B200_DEBUG', 0):
+            print(f'[rank {r}] streaming csr: bounds={bounds} eoff={eoff} stats={s} ok={ok}', flush=True)
         if not ok:
             return None
         return rowptr, colidx, s[1], bounds
@@ -395,7 +403,16 @@ class ShardedElphHashes(object):
             lo, hi = bounds[r], bounds[r + 1]
             others = [q for q in range(G) if q != r]
             peer_mask = zero_mask = local_rows = None
-            if self.exchange == 'halo' and symm is not None:
+            if self.exchange == 'halo' and symm is not None and self.csr_path == 'streaming':
+                # the list was verified symmetric: who reads my rows follows from my own CSR rows, no exchange
+                peer_mask = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=device)[:hi - lo]
+                local_rows = torch.zeros(num_nodes, dtype=torch.uint8, device=device)
+                bd = torch.tensor(bounds, dtype=torch.int64, device=device)
+                check(lib.ss_halo_from_csr(_ptr(rowptr), _ptr(colidx), hi - lo, _ptr(bd), G, r, _ptr(peer_mask),
+                                           _ptr(local_rows), _stream_ptr(device)), 'ss_halo_from_csr')
+                local_rows[lo:hi] = 1
+                zero_mask = torch.zeros_like(peer_mask)
+            elif self.exchange == 'halo' and symm is not None:
                 marks = torch.zeros((G, num_nodes), dtype=torch.uint8, device=device)
                 mine = torch.zeros(num_nodes, dtype=torch.uint8, device=device)
                 check(lib.ss_mark_rows(_ptr(colidx), nnz, _ptr(mine), _stream_ptr(device)), 'ss_mark_rows')
