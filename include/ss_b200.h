@@ -193,9 +193,10 @@ int ss_csr_sorted_bounds(const int64_t *key, int64_t n_edges, int64_t n_rows, do
 int ss_mark_rows(const int32_t *colidx, int64_t nnz, uint8_t *mark, ss_stream_t stream);
 /* The halo of a SYMMETRIC graph needs no exchange: row r of this rank is read by rank q exactly when r has an in-neighbour
  * owned by q.  From the rank's own CSR rows: peer_mask_out[r] (bit i = the i-th OTHER rank in ascending order reads row r)
- * and mark_out[c] = 1 for every neighbour c (the rows this rank reads).  bounds: device int64 [n_ranks + 1]. */
-int ss_halo_from_csr(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *bounds, int n_ranks, int rank,
-                     uint8_t *peer_mask_out, uint8_t *mark_out, ss_stream_t stream);
+ * and mark_out[c] = 1 for every neighbour c (the rows this rank reads).  bounds: device int64 [n_ranks + 1]; peer_mask_out:
+ * ZEROED by the caller, 4-byte aligned and padded to a multiple of 4 bytes (rows of one 32-bit word are updated atomically). */
+int ss_halo_from_csr(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const int64_t *bounds, int n_ranks,
+                     int rank, uint8_t *peer_mask_out, uint8_t *mark_out, ss_stream_t stream);
 /* Synchronisation-free CSR for the operator forms (the edge list already holds its self loops: ELPH.forward applies
  * add_self_loops itself, models/elph.py:186, and calls hll_prop / minhash_prop 2K times per training batch): nnz = n_edges
  * is known to the host, so nothing is read back.  Ids are validated on the device -- stats_out (device int64[4]) =

@@ -85,7 +85,7 @@ SIGNATURES = {
     'ss_csr_sorted_finish_rows': (c_int, [c_i64, c_i64, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'ss_csr_sorted_bounds': (c_int, [c_ptr, c_i64, c_i64, ctypes.c_double, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_mark_rows': (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
-    'ss_halo_from_csr': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    'ss_halo_from_csr': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_csr_bin_workspace_bytes': (c_i64, []),
     'ss_csr_bin_edges': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                  c_ptr]),

@@ -547,29 +547,62 @@ __global__ void __launch_bounds__(256) sorted_bounds_kernel(const int64_t *__res
 
 // halo of a SYMMETRIC graph from the owner's own CSR rows (no exchange): row r is read by rank q exactly when r has an
 // in-neighbour owned by q, so peer_mask[r] = OR over r's neighbours c of bit(position of owner(c) among the other
-// ranks); and every neighbour c is a row this rank reads: mark[c] = 1.  One warp per row.
+// ranks); and every neighbour c is a row this rank reads: mark[c] = 1.  Element-parallel over the neighbour list (a
+// hub row of 700k neighbours is spread over the whole grid, not walked by one warp): every 32-position window finds
+// the row of its first position by binary search, its lanes walk forward from there, lanes of one row combine their
+// bits and one of them issues the atomic OR.  peer_mask must be zeroed by the caller and padded to a multiple of 4 bytes.
 __global__ void __launch_bounds__(256) halo_from_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                                                             int64_t n_rows, const int64_t *__restrict__ bounds, int n_ranks, int rank,
-                                                             uint8_t *__restrict__ peer_mask, uint8_t *__restrict__ mark) {
+                                                             int64_t n_rows, int64_t nnz, const int64_t *__restrict__ bounds,
+                                                             int n_ranks, int rank, uint32_t *__restrict__ peer_mask_words,
+                                                             uint8_t *__restrict__ mark) {
     const int lane = threadIdx.x & 31;
-    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int b[SS_MAX_PEERS + 1];  // b[q - 1] = first row of rank q (registers: the loops below are fully unrolled)
+    int b[SS_MAX_PEERS];  // b[q - 1] = first row of rank q (registers: the loops below are fully unrolled)
 #pragma unroll
     for (int q = 1; q <= SS_MAX_PEERS; ++q) b[q - 1] = q < n_ranks ? (int)bounds[q] : 0x7fffffff;
-    for (int64_t r = gwarp; r < n_rows; r += n_warps) {
-        const int64_t s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    // a warp owns CHUNKS of 32 consecutive windows: one binary search per chunk (row of its first position), after that
+    // the running row only moves forward
+    constexpr int WINDOWS = 32;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_chunks = (nnz + 32 * WINDOWS - 1) / (32 * WINDOWS);
+    for (int64_t ch = gwarp; ch < n_chunks; ch += n_warps) {
+      const int64_t c0 = ch * (32 * WINDOWS);
+      int64_t lo = 0, hi = n_rows;  // largest r with rowptr[r] <= c0
+      while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(rowptr + mid) <= c0) lo = mid; else hi = mid;
+      }
+      int64_t base_row = lo;  // row of the current window's first position (identical on every lane)
+      for (int w = 0; w < WINDOWS; ++w) {
+        const int64_t x0 = c0 + (int64_t)w * 32;
+        if (x0 >= nnz) break;  // warp-uniform
+        const int64_t x = x0 + lane;
+        const bool live = x < nnz;
+        int64_t row = base_row;
         unsigned bits = 0;
-        for (int64_t x = s + lane; x < e; x += 32) {
+        if (live) {
+            while (row + 1 < n_rows && __ldg(rowptr + row + 1) <= x) ++row;   // short walks: rows are consecutive
             const int c = __ldg(colidx + x);
             if (mark[c] == 0) mark[c] = 1;  // test first: a row is read by many lists but marked once
             int o = 0;
 #pragma unroll
             for (int q = 0; q < SS_MAX_PEERS; ++q) o += (c >= b[q]) ? 1 : 0;
-            if (o != rank) bits |= 1u << (o < rank ? o : o - 1);
+            if (o != rank) bits = 1u << (o < rank ? o : o - 1);
         }
-        bits = __reduce_or_sync(FULL, bits);
-        if (lane == 0) peer_mask[r] = (uint8_t)bits;
+        // the next window starts in the row of this window's last live position (or one further: the walk finds out)
+        base_row = __shfl_sync(FULL, row, min(31, (int)min((int64_t)31, nnz - 1 - x0)));
+        // lanes of one row are CONSECUTIVE (positions and rows both ascend): segmented OR-scan in 5 uniform steps (every
+        // lane executes every shuffle), then the last lane of each segment publishes its row's bits
+        const int64_t key = live ? row : (int64_t)-1 - lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, bits, o);
+            const int64_t k2 = __shfl_up_sync(FULL, key, o);
+            if (lane >= o && k2 == key) bits |= t;
+        }
+        const int64_t k_next = __shfl_down_sync(FULL, key, 1);
+        if (live && bits && (lane == 31 || k_next != key)) atomicOr(peer_mask_words + (row >> 2), bits << (8 * (row & 3)));
+      }
     }
 }
 
@@ -773,16 +806,19 @@ int ss_csr_sorted_bounds(const int64_t *key, int64_t n_edges, int64_t n_rows, do
     return SS_OK;
 }
 
-int ss_halo_from_csr(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, const int64_t *bounds, int n_ranks, int rank,
-                     uint8_t *peer_mask_out, uint8_t *mark_out, ss_stream_t stream) {
+int ss_halo_from_csr(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz, const int64_t *bounds, int n_ranks,
+                     int rank, uint8_t *peer_mask_out, uint8_t *mark_out, ss_stream_t stream) {
     SS_REQUIRE(n_rows >= 0 && n_ranks >= 1 && n_ranks <= SS_MAX_PEERS + 1 && rank >= 0 && rank < n_ranks,
                "bad sizes passed to ss_halo_from_csr");
     if (n_rows == 0) return SS_OK;
     SS_REQUIRE(rowptr && colidx && bounds && peer_mask_out && mark_out, "null pointer passed to ss_halo_from_csr");
-    int64_t blocks = (n_rows + 7) / 8;
-    int64_t cap = (int64_t)ss::sm_count() * 16;
+    SS_REQUIRE(((uintptr_t)peer_mask_out & 3) == 0, "peer_mask_out must be 4-byte aligned (and padded to a multiple of 4 bytes)");
+    SS_REQUIRE(nnz >= 0, "negative nnz");
+    if (nnz == 0) return SS_OK;
+    int64_t blocks = (nnz + 8 * 1024 - 1) / (8 * 1024);  // 8 warps x one chunk of 1024 positions
+    int64_t cap = (int64_t)ss::sm_count() * 8;
     ss::halo_from_csr_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
-        rowptr, colidx, n_rows, bounds, n_ranks, rank, peer_mask_out, mark_out);
+        rowptr, colidx, n_rows, nnz, bounds, n_ranks, rank, (uint32_t *)peer_mask_out, mark_out);
     SS_LAUNCH_CHECK("halo_from_csr_kernel");
     return SS_OK;
 }

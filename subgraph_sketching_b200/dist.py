@@ -160,6 +160,8 @@ class ShardedElphHashes(object):
         self.csr_path = None    # 'streaming' | 'histogram' (which CSR build the last call took)
         self._halo_mask = None
         self._fp_keys = None
+        self._start_init = None
+        self._bounds_dev = None
         if self.world_size == 1 or self.world_size - 1 > 7:
             self.exchange = 'nccl'
 
@@ -213,15 +215,20 @@ class ShardedElphHashes(object):
             k = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in _FP_KEYS], dtype=torch.int64, device=device)
             dist.broadcast(k, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
             self._fp_keys = tuple(int(v) & ((1 << 64) - 1) for v in k.tolist())
+        eh = self.eh
+        ev = eh._event_begin(device)
         cum = torch.tensor(cumulative_shares(G, self.shares) or [0.5], dtype=torch.float64, device=device)
         cuts = torch.empty(2 * (G + 1), dtype=torch.int64, device=device)
         row_cost = 1.0 + default_row_weight(G, self.exchange)  # + 1: every row carries its self loop
         check(lib.ss_csr_sorted_bounds(_ptr(ei[0]), n_edges, num_nodes, row_cost, _ptr(cum), G - 1, _ptr(cuts),
                                        _ptr(cuts[G + 1:]), st), 'ss_csr_sorted_bounds')
         cl = [int(v) for v in cuts.tolist()]  # host read #1: sizes of the blocks
+        eh._event_end('csr.bounds', ev, device)
+        if self._start_init is not None:
+            self._start_init()
+        ev = eh._event_begin(device)
         bounds, eoff = cl[:G + 1], cl[G + 1:]
-        for i in range(1, G + 1):
-            bounds[i] = max(bounds[i], bounds[i - 1])
+        self._bounds_dev = cuts[:G + 1]  # cuts of an increasing cost function: already monotone
         lo, hi = bounds[r], bounds[r + 1]
         e_lo, e_hi = eoff[r], eoff[r + 1]
         n_loc, rows = e_hi - e_lo, hi - lo
@@ -242,6 +249,8 @@ class ShardedElphHashes(object):
                                   e_lo=e_lo)
         else:
             chunk(_ptr(ei[0, e_lo:e_hi]), _ptr(ei[1, e_lo:e_hi]), n_loc, e_lo)
+        eh._event_end('csr.stream', ev, device)
+        ev = eh._event_begin(device)
         # the verdict is global: order violations / range errors / fingerprints summed, id range max / min over ranks
         sums = st12[4:11].clone()
         ext = torch.stack([st12[0], -st12[3]])
@@ -256,6 +265,7 @@ class ShardedElphHashes(object):
         check(lib.ss_csr_sorted_finish_rows(n_loc, lo, rows, 1, cap, _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
                                             st), 'ss_csr_sorted_finish_rows')
         s = [int(v) for v in st12.tolist()]  # host read #2: the verdict (identical on every rank)
+        eh._event_end('csr.verdict', ev, device)
         del ring
         max_id, min_id = s[0], s[3]
         ok = s[8] == 0 and s[10] == 0 and (s[4], s[5]) == (s[6], s[7]) and max_id < num_nodes and (n_edges == 0 or min_id >= 0)
@@ -384,32 +394,46 @@ class ShardedElphHashes(object):
             lease = [True] if (symm is not None and self.reuse_buffers) else None
             self._lease = lease
             main = torch.cuda.current_stream(device)
-            # hop 0 does not depend on the graph: on a side stream, under the CSR build (which holds the host reads)
+            # hop 0 does not depend on the graph: on a side stream, under the CSR build.  It is launched from INSIDE the
+            # CSR build, after the row-block cuts were read back: its persistent grid fills every SM for ~4 ms, and a
+            # one-block kernel the host is waiting for (the cuts) would otherwise queue behind it
             rec0 = torch.empty((num_nodes, rb), dtype=torch.uint8, device=device)
             side = eh._side_stream(device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                ev = eh._event_begin(device)
-                eh._init_records(num_nodes, device, out=rec0)  # cheap: computed redundantly, never exchanged
-                eh._event_end('init_records', ev, device)
-                init_done = torch.cuda.Event()
-                init_done.record(side)
+            init_state = {}
+
+            def start_init():
+                if init_state:
+                    return
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ev_i = eh._event_begin(device)
+                    eh._init_records(num_nodes, device, out=rec0)  # cheap: computed redundantly, never exchanged
+                    eh._event_end('init_records', ev_i, device)
+                    init_state['done'] = torch.cuda.Event()
+                    init_state['done'].record(side)
+
+            self._start_init = start_init
             ev = eh._event_begin(device)
             try:
                 rowptr, colidx, nnz, bounds = self._local_csr(edge_index, num_nodes, device)
-            finally:
-                main.wait_event(init_done)
+            except BaseException:
+                self._start_init = None
+                start_init()
+                main.wait_event(init_state['done'])  # rec0 must not be recycled under the side stream
+                raise
+            self._start_init = None
+            start_init()  # (the histogram path never called it)
             self.bounds, self.local_nnz = bounds, nnz
             lo, hi = bounds[r], bounds[r + 1]
             others = [q for q in range(G) if q != r]
             peer_mask = zero_mask = local_rows = None
+            ev_h = eh._event_begin(device)
             if self.exchange == 'halo' and symm is not None and self.csr_path == 'streaming':
                 # the list was verified symmetric: who reads my rows follows from my own CSR rows, no exchange
-                peer_mask = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=device)[:hi - lo]
+                peer_mask = torch.zeros((hi - lo + 7) // 4 * 4, dtype=torch.uint8, device=device)[:hi - lo]
                 local_rows = torch.zeros(num_nodes, dtype=torch.uint8, device=device)
-                bd = torch.tensor(bounds, dtype=torch.int64, device=device)
-                check(lib.ss_halo_from_csr(_ptr(rowptr), _ptr(colidx), hi - lo, _ptr(bd), G, r, _ptr(peer_mask),
-                                           _ptr(local_rows), _stream_ptr(device)), 'ss_halo_from_csr')
+                check(lib.ss_halo_from_csr(_ptr(rowptr), _ptr(colidx), hi - lo, nnz, _ptr(self._bounds_dev), G, r,
+                                           _ptr(peer_mask), _ptr(local_rows), _stream_ptr(device)), 'ss_halo_from_csr')
                 local_rows[lo:hi] = 1
                 zero_mask = torch.zeros_like(peer_mask)
             elif self.exchange == 'halo' and symm is not None:
@@ -420,6 +444,8 @@ class ShardedElphHashes(object):
                 peer_mask, local_rows = halo_masks(marks, bounds, r)
                 zero_mask = torch.zeros_like(peer_mask)
                 del marks, mine
+            eh._event_end('csr.halo', ev_h, device)
+            main.wait_event(init_state['done'])
             eh._event_end('csr_build', ev, device)
             ws = None
             if symm is not None:

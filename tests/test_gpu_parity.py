@@ -2,6 +2,7 @@
 unmodified reference and against the CPU oracle on seeded inputs.  Integer sketches must be bit-exact;
 floats within 1e-6 of the magnitude involved (helpers.float_close)."""
 import io
+import os
 
 import numpy as np
 import pytest
@@ -91,6 +92,12 @@ def test_hll_count_and_bias_golden():
     assert np.array_equal(eh.hll_count(regs).numpy()[lc_rows], blob['counts'][lc_rows])
     bias = eh._estimate_bias(torch.from_numpy(blob['e']))
     flips = np.abs(bias.numpy() - blob['bias']) > 1e-5 * np.maximum(1.0, np.abs(blob['bias']))
+    # SURVEY "hard part 2": the reference picks the 6 nearest raw estimates with an unstable argsort, so a tie can flip the
+    # neighbour set; the observed count is REPORTED (pytest -s / the log), not hidden behind the 1 % allowance
+    print(f'[6-NN] {int(flips.sum())} neighbour-set flips out of {flips.size} bias estimates '
+          f'(max |delta| = {float(np.abs(bias.numpy() - blob["bias"]).max()):.3e})')
+    with open(os.path.join(os.environ.get('SS_TEST_REPORT_DIR', '/tmp'), 'ss_b200_6nn_flips.txt'), 'w') as fh:
+        fh.write(f'{int(flips.sum())} flips / {flips.size} estimates\n')
     assert flips.mean() <= 0.01, f'{flips.sum()} 6-NN neighbour-set flips out of {flips.size}'
     # estimates above 5m are untouched by the refinement (test_hashing.py:229-236)
     e = torch.tensor([5 * 256 + 1.0, 4000.0, 1e6])
