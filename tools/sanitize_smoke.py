@@ -48,7 +48,7 @@ for K in (1, 2, 3):
         assert all(torch.equal(a, b) for a, b in zip(feats[mode], feats['ldg'])), (K, mode)
     # the ELPH session: singles, pair fusion, guarded re-enqueue
     init_m, init_h = eh.initialise_minhash(n).to(dev), eh.initialise_hll(n).to(dev)
-    loops = torch.arange(n, device=dev)
+    loops = torch.arange(int(ei.max()) + 1, device=dev)  # add_self_loops(edge_index) without num_nodes (hashing.py:148)
     prev = None
     for fwd in range(4):
         he = torch.cat([ei, torch.stack([loops, loops])], dim=1)
