@@ -245,7 +245,7 @@ def test_small_helpers():
 def test_cards_with_fewer_rows_than_the_tables_raise():
     """mismatched caches (cards shorter than the hash tables): IndexError like the reference's cards[links[:, 0]],
     never an out-of-bounds read"""
-    n = 500
+    n = 512
     ei = rmat_edges(9, 8, 2).to(DEV)
     eh = ssb.ElphHashes(make_args(2))
     tables, cards = eh.build_hash_tables(n, ei)
@@ -698,9 +698,10 @@ def test_cache_round_trip_in_reference_formats(tmp_path):
     import os as _os
     assert _os.path.getsize(root + 'train_3hop_cardcache.pt') < 300 * 3 * 4 + 4096
     # ... and the twin that spares get_subgraph_features the re-upload is dropped with the tensor / on modification
-    assert eh._twin_of(host_cards, torch.device(DEV)) is not None
+    dev0 = torch.device('cuda', torch.cuda.current_device())
+    assert eh._twin_of(host_cards, dev0) is not None
     host_cards[0, 0] += 1.0
-    assert eh._twin_of(host_cards, torch.device(DEV)) is None
+    assert eh._twin_of(host_cards, dev0) is None
     f2 = cache.preprocess_subgraph_features(eh, root, 'train', links, ei, 300, load_hashes=True,
                                             cache_subgraph_features=True)     # from the hash cache
     assert torch.equal(f1, f2)
