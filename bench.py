@@ -677,7 +677,9 @@ def main():
     L_local = (link_slice(L, world, rank)[1] - link_slice(L, world, rank)[0]) if distributed else L
     lf_ms = sum(stage_ms.get('link_features', [])) / a.steps if stage_ms.get('link_features') else None
     lbytes = L_local * link_bytes(K)
-    link_roofline = {'bound': 'hbm', 'kernel': 'link_features_batched_kernel', 'algorithmic_bytes_per_step': lbytes,
+    link_roofline = {'bound': 'hbm', 'kernel': ('link_features_batched_kernel (sharded tables: remote records over NVLink)' if distributed
+                                                else ('link_features_kernel (per link)' if K == 3 else 'link_features_batched_kernel')),
+                     'algorithmic_bytes_per_step': lbytes,
                      'ms_per_step': lf_ms, 'achieved': lbytes / (lf_ms * 1e-3) / 1e9 if lf_ms else None,
                      'links_per_s_kernel_only': L_local / (lf_ms * 1e-3) if lf_ms else None, 'peak': peak}
     if link_roofline['achieved']:
