@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 13
+#define SS_ABI_VERSION 14
 
 #define SS_OK 0
 #define SS_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported P/p/K, misaligned buffer) */
@@ -190,6 +190,12 @@ int ss_csr_sorted_finish_rows(int64_t n_edges_total, int64_t row_begin, int64_t 
                               const int64_t *carry, ss_stream_t stream);
 int ss_csr_sorted_bounds(const int64_t *key, int64_t n_edges, int64_t n_rows, double row_cost, const double *cum_shares,
                          int n_cuts, int64_t *bounds_out, int64_t *edge_offsets_out, ss_stream_t stream);
+/* ss_csr_sorted_block: after a chunk has been absorbed, block_out (device int64[4]) = { row_begin, row_end, pos_begin, pos_end }
+ * of the rows that are complete now and were not in prev_block (NULL for the first): every row below the chunk's last key;
+ * final != 0: everything up to n_rows (call it after ss_csr_sorted_finish).  The block is empty once the pass has seen an
+ * order violation or a range error.  Feeds the `block` of ss_khop_merge_ex: hop 1 runs under the ingest stream. */
+int ss_csr_sorted_block(const int64_t *carry, const int64_t *rowptr, int64_t n_rows, int64_t colidx_capacity, const int64_t *stats,
+                        int final, const int64_t *prev_block, int64_t *block_out, ss_stream_t stream);
 int ss_mark_rows(const int32_t *colidx, int64_t nnz, uint8_t *mark, ss_stream_t stream);
 /* The halo of a SYMMETRIC graph needs no exchange: row r of this rank is read by rank q exactly when r has an in-neighbour
  * owned by q.  From the rank's own CSR rows: peer_mask_out[r] (bit i = the i-th OTHER rank in ascending order reads row r)
@@ -269,7 +275,14 @@ int ss_khop_merge_peers(const int64_t *rowptr, const int32_t *colidx, int64_t n_
  *               on R-MAT-24 over 8 GPUs only ~30 % of the (row, peer) pairs are ever read).  Cards are always replicated.
  *   guard       device int32 or NULL: when *guard == 0 at launch time the kernels return at once.  Lets a memoised
  *               pipeline (ELPH re-propagating an unchanged graph every batch, models/elph.py:180-218) be re-enqueued
- *               without a host synchronisation deciding whether the cached result is still valid. */
+ *               without a host synchronisation deciding whether the cached result is still valid.
+ *   block       "blocked launch": device int64[4] = { row_begin, row_end, pos_begin, pos_end } read at kernel start, so the
+ *               host can enqueue the merge of a row block BEFORE it knows the block (hop 1 of the rows whose edges have
+ *               already arrived, under the PCIe stream of a host edge list: ss_csr_sorted_block writes the descriptor).
+ *               rowptr / colidx / rec_out / cards_out are then the WHOLE graph's arrays (n_rows rows in total, nnz = an
+ *               upper bound of the neighbour positions, e.g. the colidx capacity), rowptr[row_begin] == pos_begin,
+ *               rowptr[row_end] == pos_end.  Full records, TMA engine, no peers; the workspace must hold
+ *               ss_merge_workspace_bytes(nnz) + 4 records. */
 #define SS_LAYOUT_FULL 0
 #define SS_LAYOUT_MINHASH 1
 #define SS_LAYOUT_HLL 2
@@ -295,6 +308,7 @@ typedef struct ss_merge_desc {
     void *mc_rec_out;
     float *mc_cards_out;
     const int32_t *guard;
+    const int64_t *block;   /* see "blocked launches" above; NULL = the whole problem, sized by n_rows / nnz */
 } ss_merge_desc;
 int ss_khop_merge_ex(const ss_merge_desc *desc, ss_stream_t stream);
 

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libss_b200.so')
 
-SS_ABI_VERSION = 13
+SS_ABI_VERSION = 14
 SS_FLAG_USE_ZERO_ONE = 1
 SS_FLAG_FLOOR = 2
 SS_MERGE_AUTO, SS_MERGE_TMA, SS_MERGE_LDG, SS_MERGE_GENERIC, SS_MERGE_BULK = 0, 1, 2, 3, 4
@@ -43,7 +43,8 @@ class MergeDesc(ctypes.Structure):
                 ('cards_out', ctypes.c_void_p), ('cards_stride', ctypes.c_int64), ('hc', ctypes.c_void_p),
                 ('n_peers', ctypes.c_int32), ('reserved', ctypes.c_int32),
                 ('peer_rec_out', ctypes.c_void_p), ('peer_cards_out', ctypes.c_void_p), ('peer_mask', ctypes.c_void_p),
-                ('mc_rec_out', ctypes.c_void_p), ('mc_cards_out', ctypes.c_void_p), ('guard', ctypes.c_void_p)]
+                ('mc_rec_out', ctypes.c_void_p), ('mc_cards_out', ctypes.c_void_p), ('guard', ctypes.c_void_p),
+                ('block', ctypes.c_void_p)]
 
 
 class ShardView(ctypes.Structure):
@@ -84,6 +85,7 @@ SIGNATURES = {
                                          ctypes.c_uint64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'ss_csr_sorted_finish_rows': (c_int, [c_i64, c_i64, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'ss_csr_sorted_bounds': (c_int, [c_ptr, c_i64, c_i64, ctypes.c_double, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    'ss_csr_sorted_block': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_mark_rows': (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     'ss_halo_from_csr': (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     'ss_csr_bin_workspace_bytes': (c_i64, []),
@@ -141,7 +143,7 @@ def _load():
 # that return early on empty input are counted by the caller's own bookkeeping
 KERNELS_PER_CALL = {
     'ss_init_records': 1, 'ss_pack_records': 1, 'ss_unpack_records': 1, 'ss_csr_rowptr': 4, 'ss_csr_degree_chunk': 1, 'ss_csr_rowptr_finish': 3, 'ss_csr_fill': 2, 'ss_csr_bin_edges': 1, 'ss_csr_sorted_chunk': 1, 'ss_csr_sorted_finish': 1, 'ss_csr_sorted_chunk_rows': 1, 'ss_csr_sorted_finish_rows': 1,
-    'ss_csr_sorted_bounds': 1, 'ss_mark_rows': 1, 'ss_halo_from_csr': 1, 'ss_link_features_sharded': 1,
+    'ss_csr_sorted_bounds': 1, 'ss_csr_sorted_block': 1, 'ss_mark_rows': 1, 'ss_halo_from_csr': 1, 'ss_link_features_sharded': 1,
     'ss_khop_merge': 2, 'ss_khop_merge_peers': 2, 'ss_khop_merge_ex': 2, 'ss_pack_records_ex': 1, 'ss_unpack_records_ex': 1,
     'ss_csr_build_nosync': 8, 'ss_i64_differs': 1, 'ss_prop_min_i64': 1, 'ss_prop_min_i64_guarded': 1, 'ss_prop_max_i8': 1, 'ss_hll_count': 1, 'ss_estimate_bias': 1,
     'ss_jaccard_i64': 1, 'ss_max_i8': 1, 'ss_link_features': 1, 'ss_col_sums': 1, 'ss_common_neighbour_scores': 1,

@@ -505,6 +505,23 @@ __global__ void __launch_bounds__(256) sorted_csr_finish_kernel(int64_t n_edges,
     }
 }
 
+// the rows that are COMPLETE after a chunk of a key-ordered list has been absorbed by sorted_csr_kernel: every row below
+// the chunk's last key (the row of the last key itself may continue in the next chunk).  Writes the descriptor of the
+// block [previous block's end, that row) for a blocked merge launch; `final`: everything up to n_rows (after
+// sorted_csr_finish_kernel).  If the pass has seen an order violation or a range error so far, the block is EMPTY:
+// rowptr may be garbage then and the speculative result will be discarded anyway.
+__global__ void sorted_block_kernel(const long long *carry, const int64_t *rowptr, int64_t n_rows, int64_t capacity,
+                                    const long long *stats, int final, const long long *prev, long long *block) {
+    const long long row_begin = prev ? prev[1] : 0, pos_begin = prev ? prev[3] : 0;
+    long long row_end = final ? n_rows : carry[0];
+    const bool bad = stats[8] != 0 || stats[10] != 0;
+    if (bad || row_end < row_begin) row_end = row_begin;
+    if (row_end > n_rows) row_end = n_rows;
+    long long pos_end = row_end > row_begin ? rowptr[row_end] : pos_begin;
+    if (pos_end < pos_begin || pos_end > capacity) { row_end = row_begin; pos_end = pos_begin; }
+    block[0] = row_begin; block[1] = row_end; block[2] = pos_begin; block[3] = pos_end;
+}
+
 // cost-balanced row blocks of a key-ordered list without a histogram: cost(r) = (#edges with key < r) + row_cost * r,
 // cut at the cumulative shares cum[q]; one WARP per cut, binary search over rows with a 32-ary search over the list
 // inside (key may be a pinned host pointer: ~150 dependent round trips per cut instead of ~700)
@@ -792,6 +809,16 @@ int ss_csr_sorted_finish_rows(int64_t n_edges_total, int64_t row_begin, int64_t 
         n_edges_total, row_begin, n_rows, colidx_capacity, add_self_loops ? 1 : 0, rowptr, colidx, (long long *)stats_io,
         (const long long *)carry);
     SS_LAUNCH_CHECK("sorted_csr_finish_kernel");
+    return SS_OK;
+}
+
+int ss_csr_sorted_block(const int64_t *carry, const int64_t *rowptr, int64_t n_rows, int64_t colidx_capacity, const int64_t *stats,
+                        int final, const int64_t *prev_block, int64_t *block_out, ss_stream_t stream) {
+    SS_REQUIRE(carry && rowptr && stats && block_out && n_rows >= 0, "bad arguments to ss_csr_sorted_block");
+    ss::sorted_block_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const long long *)carry, rowptr, n_rows, colidx_capacity,
+                                                              (const long long *)stats, final, (const long long *)prev_block,
+                                                              (long long *)block_out);
+    SS_LAUNCH_CHECK("sorted_block_kernel");
     return SS_OK;
 }
 

@@ -63,7 +63,46 @@ struct MergeArgs {
     const uint8_t *peer_mask;
     // memoised pipelines: skip the launch when *guard == 0 (see guarded_skip)
     const int *guard;
+    // BLOCKED launches (hop 1 under the ingest stream): the row block [row_begin, row_end) and its neighbour positions
+    // [pos_begin, pos_end) are read from DEVICE memory at kernel start -- the host enqueues the launch before it knows
+    // them.  rowptr / colidx / out / cards / scratch are then the WHOLE graph's arrays (absolute positions).
+    const long long *block;
 };
+
+// the part of the problem a launch works on: everything (host-sized) or a device-described row block
+struct MergeSpan {
+    int64_t row0, n_rows;   // rows [row0, row0 + n_rows)
+    int64_t pos0, pos1;     // neighbour positions [pos0, pos1)
+    int64_t win0, n_ranges; // first quantum-aligned window and number of windows touching [pos0, pos1)
+};
+template <bool BLOCKED>
+__device__ __forceinline__ MergeSpan merge_span(const MergeArgs &a) {
+    MergeSpan sp;
+    if (BLOCKED) {
+        sp.row0 = __ldg(a.block + 0);
+        sp.n_rows = __ldg(a.block + 1) - sp.row0;
+        sp.pos0 = __ldg(a.block + 2);
+        sp.pos1 = __ldg(a.block + 3);
+        sp.win0 = sp.pos0 / a.quantum;
+        sp.n_ranges = sp.pos1 > sp.pos0 ? (sp.pos1 - 1) / a.quantum - sp.win0 + 1 : 0;
+    } else {
+        sp.row0 = 0; sp.n_rows = a.n_rows; sp.pos0 = 0; sp.pos1 = a.nnz; sp.win0 = 0; sp.n_ranges = a.n_ranges;
+    }
+    return sp;
+}
+// arguments as the row-level helpers see them: in a blocked launch rowptr / out / cards are rebased to the block's
+// first row (rowptr VALUES stay absolute positions; range starts are absolute too)
+template <bool BLOCKED>
+__device__ __forceinline__ MergeArgs merge_rebased(const MergeArgs &a, const MergeSpan &sp) {
+    MergeArgs b = a;
+    if (BLOCKED) {
+        b.rowptr = a.rowptr + sp.row0;
+        b.n_rows = sp.n_rows;
+        b.out = a.out + sp.row0 * a.out_stride;
+        if (a.cards) b.cards = a.cards + sp.row0 * a.cards_stride;
+    }
+    return b;
+}
 
 // HLL++ estimate of a row held as 8 registers per lane.  Not inlined: it is called once per output row
 // from several places in the unrolled stream loop.
@@ -410,15 +449,18 @@ __device__ __forceinline__ void lds_words(uint32_t addr, uint32_t *w) {
     if (W == 1) { w[0] = lds_u1(addr); }
 }
 
-template <int S, int WARPS, int MIN_CTAS, bool GATHER4, int MODE>
-__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const MergeArgs a,
+template <int S, int WARPS, int MIN_CTAS, bool GATHER4, int MODE, bool BLOCKED = false>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const MergeArgs a_in,
                                                                            const __grid_constant__ CUtensorMap tmap) {
     constexpr int G = 4;
     constexpr int RB = Lay<MODE>::BYTES;
     constexpr int MW = Lay<MODE>::MW, HW = Lay<MODE>::HW;
     constexpr uint32_t STAGE = G * RB;
     extern __shared__ __align__(1024) uint8_t smem[];
-    if (guarded_skip(a.guard)) return;
+    if (guarded_skip(a_in.guard)) return;
+    const MergeSpan sp = merge_span<BLOCKED>(a_in);
+    const MergeArgs blocked_args = merge_rebased<BLOCKED>(a_in, sp);
+    const MergeArgs &a = BLOCKED ? blocked_args : a_in;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t ring = smem_u32(smem) + (uint32_t)warp * (S * STAGE);
@@ -437,20 +479,22 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
     // ring positions persist across ranges (every range drains its pipeline, so both end up equal)
     uint32_t slot_p = 0, slot_c = 0, par_c = 0;
 
-    for (int64_t w = gwarp; w < a.n_ranges; w += n_warps) {
-        const int64_t s = w * a.quantum;
-        const int n_pos = (int)min((int64_t)a.quantum, a.nnz - s);
+    for (int64_t wi = gwarp; wi < sp.n_ranges; wi += n_warps) {
+        const int64_t w = sp.win0 + wi;  // absolute window: also the index of the range's scratch slots
+        const int64_t s = BLOCKED ? max(w * a.quantum, sp.pos0) : w * a.quantum;
+        const int n_pos = (int)(min((w + 1) * (int64_t)a.quantum, sp.pos1) - s);
         if (n_pos <= 0) continue;
         const int n_groups = (n_pos + G - 1) / G;
         // s is a multiple of 32 and colidx is 16-byte aligned: the ids of a full group are one aligned int4
+        // (not in a blocked launch, whose first range starts at the block's first position: scalar loads there)
         const int32_t *__restrict__ ids_ptr = a.colidx + s;
         auto load_ids = [&](int g) {
-            if (g * G + G <= n_pos) return __ldg(reinterpret_cast<const int4 *>(ids_ptr) + g);
+            if (!BLOCKED && g * G + G <= n_pos) return __ldg(reinterpret_cast<const int4 *>(ids_ptr) + g);
             int4 r;  // ragged tail of the last range: never read past nnz; missing ids repeat the first
             r.x = __ldg(ids_ptr + g * G);
             r.y = (g * G + 1 < n_pos) ? __ldg(ids_ptr + g * G + 1) : r.x;
             r.z = (g * G + 2 < n_pos) ? __ldg(ids_ptr + g * G + 2) : r.x;
-            r.w = r.x;
+            r.w = (BLOCKED && g * G + 3 < n_pos) ? __ldg(ids_ptr + g * G + 3) : r.x;
             return r;
         };
 
@@ -528,17 +572,21 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) merge_tma_kernel(const M
 // ------------------------------------------------------------------------------------------------
 // fix-up: fold the partial records of rows cut by range boundaries; zero-fill rows with no in-edge
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a) {
+template <int MODE, bool BLOCKED = false>
+__global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeArgs a_in) {
     constexpr int RB = Lay<MODE>::BYTES;
-    if (guarded_skip(a.guard)) return;
+    if (guarded_skip(a_in.guard)) return;
+    const MergeSpan sp = merge_span<BLOCKED>(a_in);
+    const MergeArgs blocked_args = merge_rebased<BLOCKED>(a_in, sp);
+    const MergeArgs &a = BLOCKED ? blocked_args : a_in;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     // (A) one warp per range: the range in which a cut row STARTS folds all of its pieces
-    for (int64_t w = gwarp; w < a.n_ranges; w += n_warps) {
-        const int64_t s = w * a.quantum;
-        const int64_t e = min(s + (int64_t)a.quantum, a.nnz);
+    for (int64_t wi = gwarp; wi < sp.n_ranges; wi += n_warps) {
+        const int64_t w = sp.win0 + wi;
+        const int64_t s = BLOCKED ? max(w * a.quantum, sp.pos0) : w * a.quantum;
+        const int64_t e = min((w + 1) * (int64_t)a.quantum, sp.pos1);
         if (s >= e) continue;
         const int64_t last = row_of_position(a.rowptr, a.n_rows, e - 1);
         const int64_t rs = __ldg(a.rowptr + last), re = __ldg(a.rowptr + last + 1);
@@ -792,6 +840,21 @@ static int launch_tma_cfg(const MergeArgs &a, const CUtensorMap &tmap, cudaStrea
     }
 }
 
+// blocked launches: the grid cannot be trimmed to the work (only the device knows it): always the resident grid
+template <int S, int WARPS, int MIN_CTAS>
+static int launch_tma_blocked(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
+    constexpr size_t smem = (size_t)WARPS * S * 4 * Lay<LAY_FULL>::BYTES + WARPS * S * 8;
+    auto k = merge_tma_kernel<S, WARPS, MIN_CTAS, true, LAY_FULL, true>;
+    SS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = 0, rc;
+    if ((rc = resident_grid(k, WARPS * 32, smem, &grid)) != SS_OK) return rc;
+    k<<<grid, WARPS * 32, smem, st>>>(a, tmap);
+    SS_LAUNCH_CHECK("merge_tma_kernel (blocked)");
+    merge_fixup_kernel<LAY_FULL, true><<<sm_count() * 8, 256, 0, st>>>(a);
+    SS_LAUNCH_CHECK("merge_fixup_kernel (blocked)");
+    return SS_OK;
+}
+
 // narrower rows (one half of a record, or a column half): gather4 only; the ring is smaller, so more warps fit
 template <int MODE>
 static int launch_tma_narrow(const MergeArgs &a, const CUtensorMap &tmap, cudaStream_t st) {
@@ -933,6 +996,13 @@ int ss_khop_merge_ex(const ss_merge_desc *d, ss_stream_t stream) {
     a.n_peers = n_peers;
     a.peer_mask = d->peer_mask;
     a.guard = d->guard;
+    a.block = (const long long *)d->block;
+    if (d->block) {
+        SS_REQUIRE(d->layout == SS_LAYOUT_FULL && variant == SS_MERGE_TMA && n_peers == 0 && !d->mc_rec_out,
+                   "blocked launches: full records, TMA engine, single GPU");
+        // two extra windows: a block's first and last range share their window with the neighbouring blocks
+        a.n_ranges += 2;
+    }
     for (int p = 0; p < SS_MAX_PEERS; ++p) {
         a.peer_out[p] = p < n_peers ? (uint8_t *)d->peer_rec_out[p] : nullptr;
         a.peer_cards[p] = (p < n_peers && want_cards) ? d->peer_cards_out[p] : nullptr;
@@ -945,6 +1015,12 @@ int ss_khop_merge_ex(const ss_merge_desc *d, ss_stream_t stream) {
         return SS_ERR_WORKSPACE;
     }
     int grid = 0, rc;
+    if (d->block) {
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        if ((rc = ss::make_row_gather_map(&tmap, d->rec_in, in_rows, in_stride, row_bytes)) != SS_OK) return rc;
+        return ss::tma_config(nnz) == 0 ? ss::launch_tma_blocked<4, 4, 4>(a, tmap, st) : ss::launch_tma_blocked<3, 4, 6>(a, tmap, st);
+    }
     if (nnz > 0) {
         if (variant == SS_MERGE_TMA || variant == SS_MERGE_BULK) {
             CUtensorMap tmap;

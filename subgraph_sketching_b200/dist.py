@@ -386,7 +386,10 @@ class ShardedElphHashes(object):
                 if symm is None:
                     self.exchange = 'nccl'
                 elif self.exchange == 'auto':
-                    self.exchange = 'halo' if (eh.num_perm == 128 and eh.p == 8) else 'p2p'
+                    # measured on R-MAT 24 (profiles/r02_bench_*gpu.json): with ONE peer nearly every row is in its halo anyway
+                    # and the pairwise kernel's remote reads cost more than a full replication saves (138 vs 116 ms per
+                    # step at 2 GPUs); from 4 GPUs on the halo push wins (84 -> 84 ms at 4, 76 -> 54 ms at 8)
+                    self.exchange = 'halo' if (eh.num_perm == 128 and eh.p == 8 and self.world_size > 2) else 'p2p'
                 if self.exchange == 'mc' and not all(int(h.multicast_ptr) for h in list(symm[3]) + [symm[4]]):
                     raise RuntimeError('this system has no NVSwitch multicast support for symmetric memory')
             if self._lease is not None:

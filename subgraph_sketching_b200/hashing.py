@@ -196,11 +196,14 @@ def _sorted_stats_ok(s, n_edges, num_rows, symmetric_needed):
     return (not symmetric_needed) or (s[4], s[5]) == (s[6], s[7])
 
 
-def _try_sorted_csr(src, dst, n_edges, num_rows, add_loops, device, streamed_from=None, degree_side=None):
+def _try_sorted_csr(src, dst, n_edges, num_rows, add_loops, device, streamed_from=None, degree_side=None, chunk_hook=None):
     """speculative one-pass CSR for key-ordered edge lists (coalesced / to_undirected output) -> (rowptr, colidx, nnz,
     max_id) or None when the list is neither (ordered by edge_index[0] AND symmetric) nor ordered by edge_index[1].
     streamed_from: pinned host edge_index to stream through the DMA ring instead of reading src / dst;
-    degree_side(buf0, buf1, lo, hi, first): called per landed chunk (the histogram pass of the fallback rides along)."""
+    degree_side(buf0, buf1, lo, hi, first): called per landed chunk (the histogram pass of the fallback rides along);
+    chunk_hook(rowptr, colidx, capacity, stats, carry, final): called after every absorbed chunk of a streamed list and once
+    more (final=True) after the build is complete, BEFORE the verdict is known -- the caller may enqueue speculative
+    work on the rows that are complete so far (hop 1 under the ingest stream); chunk_hook(None, ...) reports the verdict."""
     cap = n_edges + (num_rows if add_loops else 0)
     colidx = torch.empty(max(cap, 4), dtype=torch.int32, device=device)
     rowptr = torch.empty(num_rows + 1, dtype=torch.int64, device=device)
@@ -219,13 +222,19 @@ def _try_sorted_csr(src, dst, n_edges, num_rows, add_loops, device, streamed_fro
                 degree_side(b0, b1, lo, hi, c) if degree_side is not None else None,
                 check(lib.ss_csr_sorted_chunk(_ptr(b0), _ptr(b1), hi - lo, lo, num_rows, loops, cap, _FP_KEYS[0],
                                               _FP_KEYS[1], _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
-                                              _stream_ptr(device)), 'ss_csr_sorted_chunk')))
+                                              _stream_ptr(device)), 'ss_csr_sorted_chunk'),
+                chunk_hook(rowptr, colidx, cap, st12, carry, False) if (chunk_hook is not None and hi < n_edges) else None))
         check(lib.ss_csr_sorted_finish(n_edges, num_rows, loops, cap, _ptr(rowptr), _ptr(colidx), _ptr(st12), _ptr(carry),
                                        st), 'ss_csr_sorted_finish')
+        if chunk_hook is not None and streamed_from is not None:
+            chunk_hook(rowptr, colidx, cap, st12, carry, True)
         s = [int(v) for v in st12.tolist()]  # the one host synchronisation of the CSR build
         if streamed_from is not None:
             del ring
-        if _sorted_stats_ok(s, n_edges, num_rows, symmetric_needed=(orient == 'src')):
+        accepted = _sorted_stats_ok(s, n_edges, num_rows, symmetric_needed=(orient == 'src'))
+        if chunk_hook is not None and streamed_from is not None:
+            chunk_hook(None, None, cap, None, None, accepted)  # the verdict
+        if accepted:
             return rowptr, colidx, s[1], s[0]
         if not (orient == 'src' and s[9] == 0 and s[10] == 0):
             break  # edge_index[1] is not ordered either
@@ -270,7 +279,7 @@ def _streamed_degree_pass(ei, n_edges, row_begin, num_rows, src32, dst32, stats,
     return _stream_chunks(ei, n_edges, device, consume, e_lo=e_lo)
 
 
-def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bounds_fn=None):
+def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bounds_fn=None, chunk_hook=None):
     """COO edge_index [2, E] -> (rowptr int64 [n_rows+1], colidx int32 [>= nnz], nnz, max_id) keyed by destination
     (PyG flow source -> target, hashing.py:30-35).  With add_loops, a self loop is appended for every node id
     < max(edge_index)+1 (computed on the device), which is add_self_loops(edge_index) without num_nodes
@@ -304,7 +313,7 @@ def build_csr(edge_index, device, num_rows=None, add_loops=True, row_begin=0, bo
                                               _ptr(dst32[lo:hi]), _ptr(stats), _ptr(ws), ws.numel(), 1 if c == 0 else 0,
                                               _stream_ptr(device)), 'ss_csr_degree_chunk')
         got = _try_sorted_csr(src, dst, n_edges, num_rows, add_loops, device, streamed_from=ei if streamed else None,
-                              degree_side=side)
+                              degree_side=side, chunk_hook=chunk_hook if streamed else None)
         if got is not None:
             return got
         histogram_done = streamed
@@ -654,6 +663,19 @@ class ElphHashes(object):
         self._event_end('khop_merge', ev, device)
         return ws
 
+    def _merge_block(self, rowptr, colidx, n_rows, capacity, rec_in, rec_out, cards_col, ws, block, device):
+        """hop merge of the row block described ON THE DEVICE by `block` (ss_khop_merge_ex, blocked launch)"""
+        d = _lib.MergeDesc()
+        d.rowptr, d.colidx, d.n_rows, d.nnz = rowptr.data_ptr(), colidx.data_ptr(), n_rows, capacity
+        d.rec_in, d.in_rows, d.in_stride = rec_in.data_ptr(), rec_in.shape[0], rec_in.stride(0)
+        d.rec_out, d.out_stride = rec_out.data_ptr(), rec_out.stride(0)
+        d.num_perm, d.hll_p, d.layout, d.variant = self.num_perm, self.p, _lib.SS_LAYOUT_FULL, _lib.SS_MERGE_TMA
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        hc = self._consts(device)['hc']
+        d.cards_out, d.cards_stride, d.hc = cards_col.data_ptr(), cards_col.stride(0), ctypes.addressof(hc)
+        d.block = block.data_ptr()
+        check(lib.ss_khop_merge_ex(ctypes.byref(d), _stream_ptr(device)), 'ss_khop_merge_ex')
+
     def _event_begin(self, device):
         if self.event_log is None:
             return None
@@ -715,16 +737,40 @@ class ElphHashes(object):
                     self._event_end('init_records', ev, device)
                     init_done = torch.cuda.Event()
                     init_done.record(side)
+            cards = torch.zeros((num_nodes, self.max_hops), dtype=torch.float32, device=device)
+            # Hop 1 under the ingest stream: in a source-ordered list every row below a landed chunk's last key is
+            # complete, so its hop-1 merge (hop 0 does not depend on the graph) runs while the rest of the list is still
+            # crossing PCIe.  Speculative like the streaming CSR itself: discarded if the list turns out ineligible.
+            hop1 = {'prev': None, 'keep': [], 'ws': None, 'accepted': False, 'ran': False}
+            want_hop1 = (init_done is not None and num_nodes > 0 and self.num_perm == 128 and self.p == 8
+                         and self.merge_variant in ('auto', 'tma') and _env_int('SS_B200_INGEST_OVERLAP', 1))
+
+            def chunk_hook(rp, ci, cap, st12, carry, final):
+                if rp is None:
+                    hop1['accepted'] = bool(final) and hop1['ran']
+                    return
+                if not hop1['ran']:
+                    main.wait_event(init_done)  # hop 0 (side stream, ~4 ms) is long done when the first chunk has landed
+                    need = check(lib.ss_merge_workspace_bytes(cap, self.num_perm, self.p), 'ss_merge_workspace_bytes') + 4 * rb
+                    hop1['ws'] = torch.empty(need, dtype=torch.uint8, device=device)
+                    hop1['ran'] = True
+                blk = torch.empty(4, dtype=torch.int64, device=device)
+                check(lib.ss_csr_sorted_block(_ptr(carry), _ptr(rp), num_nodes, cap, _ptr(st12), 1 if final else 0,
+                                              _ptr(hop1['prev']), _ptr(blk), _stream_ptr(device)), 'ss_csr_sorted_block')
+                self._merge_block(rp, ci, num_nodes, cap, recs[0], recs[1], cards[:, 0], hop1['ws'], blk, device)
+                hop1['prev'] = blk
+                hop1['keep'].append(blk)
+
             ev = self._event_begin(device)
             try:
-                rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=num_nodes, add_loops=True)
+                rowptr, colidx, nnz, max_id = build_csr(edge_index, device, num_rows=num_nodes, add_loops=True,
+                                                        chunk_hook=chunk_hook if want_hop1 else None)
             finally:  # also on the error paths: the table memory must not be recycled under the side stream
                 if init_done is not None:
                     main.wait_event(init_done)
             self._event_end('csr_build', ev, device)
             if max_id >= num_nodes:
                 raise IndexError(f'edge_index refers to node {max_id} but num_nodes is {num_nodes}')
-            cards = torch.zeros((num_nodes, self.max_hops), dtype=torch.float32, device=device)
             ws = None
             for k in range(self.max_hops + 1):
                 logger.info(f"Calculating hop {k} hashes")
@@ -733,6 +779,8 @@ class ElphHashes(object):
                         ev = self._event_begin(device)
                         self._init_records(num_nodes, device, out=recs[0])
                         self._event_end('init_records', ev, device)
+                elif k == 1 and hop1['accepted']:
+                    continue  # merged block by block while the edge list was still arriving
                 elif num_nodes > 0:
                     ws = self._merge(rowptr, colidx, nnz, recs[k - 1], recs[k], cards[:, k - 1], device, ws)
             logger.info(f'hash generation enqueued in {time() - start} s')

@@ -807,6 +807,36 @@ def test_streaming_csr_of_key_ordered_lists(monkeypatch):
         assert calls == [eligible], (name, calls)
         assert got[2] == want[2] and torch.equal(got[0], want[0]), name
         assert torch.equal(_adjacency_key(got, n), _adjacency_key(want, n)), name
+    # hop 1 under the ingest stream: a streamed, eligible list has its hop-1 rows merged block by block while later
+    # chunks are still arriving (blocked launches described on the device); hubs span several 1024-edge chunks here.
+    # Same tables, cards and features as the device-resident build; an ineligible list discards the speculative hop.
+    monkeypatch.setattr(H, 'INGEST_CHUNK', 1 << 10)
+    monkeypatch.setenv('SS_B200_CSR_FAST', '1')
+    g2 = torch.Generator().manual_seed(11)
+    lk = torch.randint(0, n, (5000, 2), generator=g2).to(dev)
+    for K in (1, 3):
+        eh = ssb.ElphHashes(make_args(K))
+        t_dev, c_dev = eh.build_hash_tables(n, sym)
+        f_dev = eh.get_subgraph_features(lk, t_dev, c_dev)
+        blocks = []
+        real_block = eh._merge_block
+        eh._merge_block = lambda *a, **kw: (blocks.append(1), real_block(*a, **kw))[1]
+        for name, expect_blocks in (('symmetric', True), ('isolated runs', True), ('asymmetric ordered by src', True), ('shuffled', True)):
+            ei_h = cases[name][0].cpu().pin_memory()
+            blocks.clear()
+            t_h, c_h = eh.build_hash_tables(n, ei_h)
+            assert bool(blocks) == expect_blocks, (name, len(blocks))
+            t_ref, c_ref = (t_dev, c_dev) if name == 'symmetric' else eh.build_hash_tables(n, cases[name][0])
+            for k in range(K + 1):
+                assert torch.equal(t_h.records(k), t_ref.records(k)), (K, name, k)
+            assert torch.equal(c_h.to(dev), c_ref), (K, name)
+            if name == 'symmetric':
+                assert torch.equal(eh.get_subgraph_features(lk, t_h, c_h.to(dev)), f_dev)
+        monkeypatch.setenv('SS_B200_INGEST_OVERLAP', '0')
+        blocks.clear()
+        t_h, c_h = eh.build_hash_tables(n, cases['symmetric'][0].cpu().pin_memory())
+        assert not blocks and torch.equal(t_h.records(K), t_dev.records(K))
+        monkeypatch.delenv('SS_B200_INGEST_OVERLAP')
     # out-of-range ids still raise through the fallback
     bad = sym.clone()
     bad[1, -1] = n + 5
