@@ -12,7 +12,7 @@ blocks gave rank 0 74 % of the edges of an R-MAT-24 graph at 2 ranks), so the bl
 cost(block) = neighbours + row_weight * rows, then adapted from the merge times each rank measured.
 
 Exchange modes (`exchange=`)
-  'halo' (default when symmetric memory works): the hop tables live in symmetric memory
+  'halo' (what 'auto' picks beyond 4 GPUs): the hop tables live in symmetric memory
          (torch.distributed._symmetric_memory: every rank's buffer is mapped into every process over NVLink) and the
          merge kernel itself stores each finished row into the tables of exactly those peers whose neighbour lists
          read it (ss_khop_merge_ex `peer_mask`; the mask comes from one all-gather of per-rank "rows I read" byte
@@ -25,7 +25,8 @@ Exchange modes (`exchange=`)
   'mc'   like 'p2p', but every store is ONE multimem.st to the NVSwitch multicast address of the buffer.
   'nccl' one torch.distributed broadcast per owner block after the merge kernel (works everywhere).
 'p2p' / 'mc' / 'nccl' return fully replicated tables (every rank can index any row, as the reference's API
-promises); 'halo' is what the feature pipeline wants.  No NCCL call sits on the per-hop data path of the three
+promises); 'auto' replicates up to 4 GPUs (p2p at 2, multicast at 3-4: measured faster there, see build_hash_tables) and
+switches to 'halo' beyond.  No NCCL call sits on the per-hop data path of the three
 symmetric-memory modes: hops are separated by a stream-ordered symmetric-memory barrier.
 
 Edge lists that are ordered by source and symmetric (PyG coalesce / to_undirected output, what the reference
@@ -386,10 +387,16 @@ class ShardedElphHashes(object):
                 if symm is None:
                     self.exchange = 'nccl'
                 elif self.exchange == 'auto':
-                    # measured on R-MAT 24 (profiles/r02_bench_*gpu.json): with ONE peer nearly every row is in its halo anyway
-                    # and the pairwise kernel's remote reads cost more than a full replication saves (138 vs 116 ms per
-                    # step at 2 GPUs); from 4 GPUs on the halo push wins (84 -> 84 ms at 4, 76 -> 54 ms at 8)
-                    self.exchange = 'halo' if (eh.num_perm == 128 and eh.p == 8 and self.world_size > 2) else 'p2p'
+                    # measured on R-MAT 24, K=3, 20 M links (profiles/r02_bench_*gpu.json), ms per step:
+                    #   GPUs   replicate (p2p / mc)   halo
+                    #    2        108.2 (p2p)         138.5    one peer: nearly every row is in its halo anyway, and the
+                    #    4         80.0 (mc)           83.9    pairwise kernel's remote reads cost more than replication
+                    #    8         75.7 (mc, round 1)  54.0    from 8 GPUs on every GPU ingesting the whole table loses
+                    has_mc = all(int(h.multicast_ptr) for h in list(symm[3]) + [symm[4]])
+                    if eh.num_perm == 128 and eh.p == 8 and self.world_size > 4:
+                        self.exchange = 'halo'
+                    else:
+                        self.exchange = 'mc' if (has_mc and self.world_size > 2) else 'p2p'
                 if self.exchange == 'mc' and not all(int(h.multicast_ptr) for h in list(symm[3]) + [symm[4]]):
                     raise RuntimeError('this system has no NVSwitch multicast support for symmetric memory')
             if self._lease is not None:
