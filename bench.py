@@ -388,7 +388,7 @@ def run_ogb_config(name, a, g, device, peak, do_check, rank, world, dist_engine=
     else:
         eng = eh = ssb.ElphHashes(engine_args(K))
         lo, hi = 0, L
-    my_links = links if dist_engine is not None else links  # the sharded engine slices the full list itself
+    my_links = links  # (the sharded engine slices the full list itself)
     bsz = batch or L
 
     def features(tables, cards, lk):
