@@ -331,12 +331,9 @@ __device__ __forceinline__ int lk_select3(int idx, int a0, int a1, int a2) { ret
 __device__ __forceinline__ void lk_cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void lk_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void lk_cp_async4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void lk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void lk_cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void lk_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // which rank owns row `node` (row blocks are contiguous: bounds[q] <= node < bounds[q + 1])
@@ -502,10 +499,6 @@ __device__ __forceinline__ void lk_finish_batch(const LinkArgs &a, const LkSlot 
         __syncwarp();
         for (int x = lane; x < nb * F; x += 32) a.features[i0 * F + x] = stage[x];
     }
-}
-
-__device__ __forceinline__ void lk_cp_async8(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 
 // Shared memory of one warp (dynamic, carved by lk_smem_per_warp):

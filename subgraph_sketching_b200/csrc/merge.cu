@@ -33,7 +33,6 @@
 namespace ss {
 
 constexpr int REC = 768;       // default record: 512 B MinHash + 256 B HLL
-constexpr int REC_MH = 512;
 
 struct MergeArgs {
     const int64_t *rowptr;
