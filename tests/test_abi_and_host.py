@@ -182,3 +182,23 @@ def test_packaged_hllpp_tables_warn_and_are_labelled(monkeypatch):
     thr, est, bias = H.hllpp_tables(8)
     eh2 = ssb.ElphHashes(make_args(), hll_tables=(thr, est, bias))
     assert eh2.hll_tables_source == 'caller'
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/ss_b200.h compiles as C99 (no C++ in the boundary) and the structs passed by pointer have the same size
+    in C and in the ctypes binding (a field added on one side only would shift everything behind it)"""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'abi.c'
+    src.write_text('#include "ss_b200.h"\n#include <stdio.h>\nint main(void) { printf("%zu %zu %zu %zu %d\\n", '
+                   'sizeof(ss_merge_desc), sizeof(ss_shard_view), sizeof(ss_hll_consts), sizeof(ss_hop_view), '
+                   'SS_ABI_VERSION); return 0; }\n')
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [ctypes.sizeof(_lib.MergeDesc), ctypes.sizeof(_lib.ShardView),
+                                     ctypes.sizeof(_lib.HllConsts), ctypes.sizeof(_lib.HopView), _lib.SS_ABI_VERSION]
